@@ -1,0 +1,121 @@
+/* qocgrape.h — C ABI of libqocgrape.so: B200-native (sm_100a) GRAPE fidelity + gradient evaluation.
+ *
+ * This is the drop-in boundary for ONE hot path of QuOptimalControl.jl.  The reference has no FFI of its
+ * own (it is pure Julia); each entry point below states the reference routine it replaces
+ * (paths relative to /root/reference/).  The Julia glue that binds these with `ccall`
+ * (struct GPUGRAPE + solve methods) is shown in INTEGRATION.md; the same ABI is driven from Python ctypes by
+ * quoptimalcontrol.jl_b200/_lib.py.
+ *
+ * Conventions (identical to the reference's in-memory data, so no transposes on either side):
+ *   - complex numbers are interleaved (re, im) doubles == Julia ComplexF64 == C `double _Complex`;
+ *   - matrices are column-major D x D;
+ *   - a pulse x is Julia's K x N column-major `control_array[j, i]` (control j, slice i): x[j + i*K];
+ *     the gradient has the same shape;
+ *   - every function returns a status (0 = QOC_OK); no exception crosses the boundary;
+ *   - the library copies inputs during the call and never retains host pointers;
+ *   - a handle is used by one thread at a time; different handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device or for unsupported shapes an error is returned.
+ */
+#ifndef QOCGRAPE_H
+#define QOCGRAPE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QOC_OK 0
+#define QOC_EINVAL 1        /* bad argument / shape */
+#define QOC_ECUDA 2         /* CUDA runtime error (see qoc_last_error) */
+#define QOC_ENOMEM 3        /* device workspace does not fit */
+#define QOC_EUNSUPPORTED 4  /* shape or mode not implemented by the CUDA path */
+
+/* src/problems.jl:8-10 — StateTransfer / UnitaryGate / CoherenceTransfer (README's ClosedStateTransfer /
+ * UnitarySynthesis / OpenSystemCoherenceTransfer) */
+#define QOC_STATE_TRANSFER 0
+#define QOC_UNITARY_GATE 1
+#define QOC_COHERENCE_TRANSFER 2
+
+/* gradient: first order = grad_func!/grad_func (src/GRAPE.jl:261-303); exact = real(Zygote.gradient) of the
+ * ADGRAPE functional (src/GRAPE.jl:14-18, src/solve.jl:268-290), computed by Frechet derivatives. */
+#define QOC_GRAD_FIRST_ORDER 0
+#define QOC_GRAD_EXACT 1
+
+/* first-order sign convention for UnitaryGate: in-place grad_func! (+i dt, src/GRAPE.jl:272) or static
+ * grad_func (-i dt, src/GRAPE.jl:290).  Ignored otherwise. */
+#define QOC_REF_INPLACE 0
+#define QOC_REF_STATIC 1
+
+/* shared_flags for qoc_set_system: the argument holds ONE matrix (set) used by all M members */
+#define QOC_SHARED_A 1
+#define QOC_SHARED_B 2
+#define QOC_SHARED_XI 4
+#define QOC_SHARED_XT 8
+
+typedef struct qoc_handle qoc_handle;
+
+typedef struct qoc_desc {
+  int sys_type;      /* QOC_STATE_TRANSFER | QOC_UNITARY_GATE | QOC_COHERENCE_TRANSFER */
+  int D;             /* matrix dimension (Hilbert or Liouville) */
+  int K;             /* n_controls (Problem.n_controls, src/problems.jl:25) */
+  int N;             /* n_slices (Piecewise.n_slices, src/timeevolution.jl:11-14) */
+  int M;             /* ensemble members (EnsembleProblem.n_ens, src/problems.jl:35); 1 for a plain Problem */
+  int R;             /* independent pulses evaluated per call (multi-start batch); 1 for solve() */
+  double T;          /* pulse duration (Problem.T) ; dt = T/N (src/GRAPE.jl:42) */
+  int gradient;      /* QOC_GRAD_FIRST_ORDER | QOC_GRAD_EXACT */
+  int convention;    /* QOC_REF_INPLACE | QOC_REF_STATIC */
+  int device;        /* CUDA device ordinal */
+  double expm_theta; /* scaling threshold of the degree-8 Taylor exponential; <= 0 selects the default
+                        (0.0694: truncation error below 2^-53) */
+  int flags;         /* reserved, 0 */
+} qoc_desc;
+
+typedef struct qoc_stats {
+  long long n_evals;          /* calls of qoc_eval / qoc_eval_device */
+  long long n_launches;       /* kernels launched by this handle so far */
+  int launches_last_eval;     /* kernels launched by the most recent evaluation */
+  float gpu_ms_last_eval;     /* device time of the most recent qoc_eval (CUDA events), 0 for eval_device */
+  long long workspace_bytes;  /* device memory held */
+  int path;                   /* 1 = warp-resident DMMA (D <= 16), 2 = tiled DMMA GEMM (D > 16) */
+} qoc_stats;
+
+const char* qoc_version(void);
+
+/* Allocates device workspace for the shape in `desc`.  Replaces init_GRAPE (src/grape_tools.jl:4-16). */
+int qoc_create(qoc_handle** out, const qoc_desc* desc);
+int qoc_destroy(qoc_handle* h);
+
+/* Uploads the problem(s): Problem.A/B/Xi/Xt (src/problems.jl:19-28), or for an ensemble the M member problems
+ * produced by init_ensemble (src/tools.jl:42-53) and EnsembleProblem.wts.
+ *   A  [M][D*D]      (or [D*D] with QOC_SHARED_A)
+ *   B  [M][K][D*D]   (or [K][D*D] with QOC_SHARED_B)
+ *   Xi [M][D*D], Xt [M][D*D] (or single with the SHARED flags)
+ *   wts [M] or NULL (all 1.0; a plain Problem is M = 1, weight 1). */
+int qoc_set_system(qoc_handle* h, const double* A, const double* B, const double* Xi, const double* Xt,
+                   const double* wts, int shared_flags);
+
+/* One fidelity+gradient evaluation per pulse: the body of the Optim.only_fg! closure
+ * (src/solve.jl:75-100 single problem, :164-196 ensemble) = _fom_and_gradient_GRAPE! (src/GRAPE.jl:25-96)
+ * over all members, weighted and summed.
+ *   x [R][N*K] host;  F [R] or NULL;  G [R][N*K] or NULL (value-only evaluation skips the backward sweep). */
+int qoc_eval(qoc_handle* h, const double* x, double* F, double* G);
+
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the handle's
+ * stream): x_dev [R][N*K];  FG_dev [R][1 + N*K] with F first, then G.  Lets one-process-per-GPU callers
+ * all-reduce FG_dev (NCCL) without a host round trip. */
+int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);
+
+/* pw_evolve (src/timeevolution.jl:28-39) with U0 = I:  U [R][M][D*D] = P_N ... P_1. */
+int qoc_total_propagator(qoc_handle* h, const double* x, double* U);
+
+/* pw_prop_save! (src/timeevolution.jl:98-110) for mode 0, pw_ham_save! (:64-75) for mode 1,
+ * pw_gen_save! (:80-92) for mode 2:  out [R][M][N][D*D]. */
+int qoc_propagators(qoc_handle* h, const double* x, double* out, int mode);
+
+int qoc_get_stats(qoc_handle* h, qoc_stats* out);
+/* Message of the last error on this handle (or of the last failed qoc_create when h == NULL). */
+const char* qoc_last_error(qoc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QOCGRAPE_H */

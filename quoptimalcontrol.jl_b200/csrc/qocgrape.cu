@@ -1,0 +1,415 @@
+// libqocgrape.so — host orchestration + C ABI (include/qocgrape.h).  No CPU fallback anywhere: every
+// entry point either runs the sm_100a kernels or returns an error.
+#include "../../include/qocgrape.h"
+#include "small_d.cuh"
+#include "big_d.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace qoc;
+
+static thread_local std::string g_create_error;
+
+struct qoc_handle {
+  qoc_desc d{};
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // derived small-path geometry
+  int path = 0, NB = 1, CPW = 1, pack_mode = 0, n_groups = 0, n_inner = 0, n_sysgroups = 0, nmat = 0;
+  int have_P = 0, sys_in_smem = 0, smem_bytes = 0;
+  int NK = 0, red_chunk = 0, red_nchunks = 0;
+  bool system_set = false;
+  // device buffers
+  double2 *sys = nullptr, *xi = nullptr, *xt = nullptr, *ident = nullptr, *storeP = nullptr, *storeS = nullptr;
+  double *wts = nullptr, *x = nullptr, *fomc = nullptr, *gradc = nullptr, *part = nullptr, *out = nullptr;
+  double2* staging = nullptr;   // raw caller matrices on device (set_system) / outputs of propagator calls
+  size_t staging_bytes = 0;
+  double *hx = nullptr, *hout = nullptr;   // pinned host staging
+  long long ws_bytes = 0;
+  qoc_stats st{};
+  BigState* big = nullptr;
+};
+
+#define QOC_CUDA(h, call)                                                                           \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+      return e_ == cudaErrorMemoryAllocation ? QOC_ENOMEM : QOC_ECUDA;                              \
+    }                                                                                               \
+  } while (0)
+
+template <class T> static int dev_alloc(qoc_handle* h, T** p, size_t n) {
+  if (n == 0) n = 1;
+  QOC_CUDA(h, cudaMalloc((void**)p, n * sizeof(T)));
+  h->ws_bytes += (long long)(n * sizeof(T));
+  return QOC_OK;
+}
+
+extern "C" const char* qoc_version(void) { return "qocgrape-b200 0.1 (sm_100a, DMMA)"; }
+
+extern "C" const char* qoc_last_error(qoc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+// ------------------------------------------------------------------------------------------------ dispatch
+typedef void (*chain_fn)(const SmallParams);
+template <int NB, int CPW> static chain_fn pick_chain2(int sys, int grad) {
+  if (sys == SYS_UNITARY) {
+    if (grad == GRAD_NONE) return chain_kernel<NB, CPW, SYS_UNITARY, GRAD_NONE>;
+    if (grad == GRAD_FIRST) return chain_kernel<NB, CPW, SYS_UNITARY, GRAD_FIRST>;
+    return chain_kernel<NB, CPW, SYS_UNITARY, GRAD_EXACT>;
+  }
+  if (grad == GRAD_NONE) return chain_kernel<NB, CPW, SYS_DENSITY, GRAD_NONE>;
+  if (grad == GRAD_FIRST) return chain_kernel<NB, CPW, SYS_DENSITY, GRAD_FIRST>;
+  return chain_kernel<NB, CPW, SYS_DENSITY, GRAD_EXACT>;
+}
+static chain_fn pick_chain(int NB, int CPW, int sys, int grad) {
+  if (NB == 2) return pick_chain2<2, 1>(sys, grad);
+  if (CPW == 4) return pick_chain2<1, 4>(sys, grad);
+  if (CPW == 2) return pick_chain2<1, 2>(sys, grad);
+  return pick_chain2<1, 1>(sys, grad);
+}
+typedef void (*slice_fn)(const SliceParams);
+static slice_fn pick_slices(int NB, int CPW) {
+  if (NB == 2) return expm_slices_kernel<2, 1>;
+  if (CPW == 4) return expm_slices_kernel<1, 4>;
+  if (CPW == 2) return expm_slices_kernel<1, 2>;
+  return expm_slices_kernel<1, 1>;
+}
+
+static int launch_check(qoc_handle* h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = std::string(what) + ": " + cudaGetErrorString(e); return QOC_ECUDA; }
+  h->st.n_launches++; h->st.launches_last_eval++;
+  return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ create
+extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
+  if (!out || !desc) { g_create_error = "qoc_create: null argument"; return QOC_EINVAL; }
+  *out = nullptr;
+  const qoc_desc& d = *desc;
+  if (d.D < 1 || d.K < 0 || d.N < 1 || d.M < 1 || d.R < 1 || !(d.T == d.T) ||
+      d.sys_type < 0 || d.sys_type > 2 || d.gradient < 0 || d.gradient > 1 || d.convention < 0 || d.convention > 1) {
+    g_create_error = "qoc_create: invalid descriptor"; return QOC_EINVAL;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("qoc_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback";
+    return QOC_ECUDA;
+  }
+  if (d.device < 0 || d.device >= ndev) { g_create_error = "qoc_create: bad device ordinal"; return QOC_EINVAL; }
+  qoc_handle* h = new qoc_handle();
+  h->d = d;
+  if (h->d.expm_theta <= 0) h->d.expm_theta = T8_THETA_DEFAULT;
+  h->NK = d.N * d.K;
+  auto fail = [&](int rc) { g_create_error = h->err; qoc_destroy(h); return rc; };
+#define CR(call) do { int rc_ = (call); if (rc_ != QOC_OK) return fail(rc_); } while (0)
+#define CRC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(e_ == cudaErrorMemoryAllocation ? QOC_ENOMEM : QOC_ECUDA); } } while (0)
+  CRC(cudaSetDevice(d.device));
+  CRC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CRC(cudaEventCreate(&h->ev0));
+  CRC(cudaEventCreate(&h->ev1));
+
+  const size_t DD = (size_t)d.D * d.D;
+  if (d.D <= 16) {
+    h->path = 1;
+    if (d.D <= 2) { h->NB = 1; h->CPW = 4; }
+    else if (d.D <= 4) { h->NB = 1; h->CPW = 2; }
+    else if (d.D <= 8) { h->NB = 1; h->CPW = 1; }
+    else { h->NB = 2; h->CPW = 1; }
+    h->pack_mode = (d.M < h->CPW && d.R > 1) ? 1 : 0;
+    if (h->pack_mode == 0) { h->n_inner = (d.M + h->CPW - 1) / h->CPW; h->n_groups = d.R * h->n_inner; h->n_sysgroups = h->n_inner; }
+    else { h->n_inner = d.M; h->n_groups = ((d.R + h->CPW - 1) / h->CPW) * d.M; h->n_sysgroups = d.M; }
+    h->nmat = 1 + d.K + (d.gradient == QOC_GRAD_EXACT ? d.K : 0);
+    h->have_P = h->n_groups < 148 * 8;   // too few chains to fill the GPU: exponentials go slice-parallel
+    const size_t E = (size_t)h->NB * h->NB * 64;
+    size_t smem = (size_t)4 * h->nmat * E * sizeof(double2);
+    h->sys_in_smem = smem <= 96 * 1024;
+    h->smem_bytes = h->sys_in_smem ? (int)smem : 0;
+    CR(dev_alloc(h, &h->sys, (size_t)h->n_sysgroups * h->nmat * E));
+    CR(dev_alloc(h, &h->xi, (size_t)h->n_sysgroups * E));
+    CR(dev_alloc(h, &h->xt, (size_t)h->n_sysgroups * E));
+    CR(dev_alloc(h, &h->ident, (size_t)h->n_sysgroups * E));
+    CR(dev_alloc(h, &h->storeP, (size_t)h->n_groups * d.N * E));
+    CR(dev_alloc(h, &h->storeS, (size_t)h->n_groups * d.N * E));
+    CR(dev_alloc(h, &h->fomc, (size_t)d.R * d.M));
+    CR(dev_alloc(h, &h->gradc, (size_t)d.R * d.M * h->NK));
+  } else {
+    h->path = 2;
+    int rc = big_create(&h->big, d, h->err, h->ws_bytes);
+    if (rc != QOC_OK) return fail(rc);
+  }
+  h->red_chunk = 64;
+  h->red_nchunks = (d.M + h->red_chunk - 1) / h->red_chunk;
+  CR(dev_alloc(h, &h->wts, (size_t)d.M));
+  CR(dev_alloc(h, &h->x, (size_t)d.R * h->NK));
+  CR(dev_alloc(h, &h->part, (size_t)d.R * h->red_nchunks * (h->NK + 1)));
+  CR(dev_alloc(h, &h->out, (size_t)d.R * (h->NK + 1)));
+  h->staging_bytes = (size_t)d.M * (size_t)(d.K > 1 ? d.K : 1) * DD * sizeof(double2);
+  CR(dev_alloc(h, (char**)&h->staging, h->staging_bytes));
+  CRC(cudaMallocHost((void**)&h->hx, (size_t)d.R * (h->NK > 0 ? h->NK : 1) * sizeof(double)));
+  CRC(cudaMallocHost((void**)&h->hout, (size_t)d.R * (h->NK + 1) * sizeof(double)));
+#undef CR
+#undef CRC
+  h->st.path = h->path;
+  h->st.workspace_bytes = h->ws_bytes;
+  *out = h;
+  return QOC_OK;
+}
+
+extern "C" int qoc_destroy(qoc_handle* h) {
+  if (!h) return QOC_OK;
+  cudaSetDevice(h->d.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->big) big_destroy(h->big);
+  void* bufs[] = {h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (h->hx) cudaFreeHost(h->hx);
+  if (h->hout) cudaFreeHost(h->hout);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ set_system
+static int pack_one(qoc_handle* h, const double2* src_dev, int n_src, long src_stride, int transpose,
+                    double2* dst, int nmat_dst, int mat_dst, int pack_mode) {
+  PackParams pp;
+  pp.D = h->d.D; pp.NB = h->NB; pp.CPW = h->CPW; pp.n_og = h->n_sysgroups; pp.nmat_dst = nmat_dst; pp.mat_dst = mat_dst;
+  pp.transpose = transpose; pp.pack_mode = pack_mode; pp.n_src = n_src; pp.src_stride = src_stride; pp.src = src_dev; pp.dst = dst;
+  long total = (long)h->n_sysgroups * h->NB * h->NB * 64;
+  pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(pp);
+  return launch_check(h, "pack_kernel");
+}
+
+extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, const double* Xi, const double* Xt,
+                              const double* wts, int shared_flags) {
+  if (!h) return QOC_EINVAL;
+  if (!A || !Xi || !Xt || (h->d.K > 0 && !B)) { h->err = "qoc_set_system: null matrix argument"; return QOC_EINVAL; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  const qoc_desc& d = h->d;
+  const size_t DD = (size_t)d.D * d.D;
+  std::vector<double> w(d.M, 1.0);
+  if (wts) memcpy(w.data(), wts, sizeof(double) * d.M);
+  QOC_CUDA(h, cudaMemcpyAsync(h->wts, w.data(), sizeof(double) * d.M, cudaMemcpyHostToDevice, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->path == 2) {
+    int rc = big_set_system(h->big, A, B, Xi, Xt, shared_flags, h->err);
+    if (rc == QOC_OK) h->system_set = true;
+    return rc;
+  }
+  // small path: stage raw matrices on the device, then pack into the warp layout
+  const int member_mode = h->pack_mode;   // 0: slot -> member og*CPW+s ; 1: all slots -> member og
+  auto upload = [&](const double* src, size_t count) -> int {
+    QOC_CUDA(h, cudaMemcpyAsync(h->staging, src, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    return QOC_OK;
+  };
+  int rc;
+  {  // A
+    bool sh = shared_flags & QOC_SHARED_A;
+    if ((rc = upload(A, (sh ? 1 : (size_t)d.M) * DD)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->sys, h->nmat, 0, member_mode)) != QOC_OK) return rc;
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (d.K > 0) {  // B (and transposed copies for the exact gradient)
+    bool sh = shared_flags & QOC_SHARED_B;
+    if ((rc = upload(B, (sh ? 1 : (size_t)d.M) * d.K * DD)) != QOC_OK) return rc;
+    for (int c = 0; c < d.K; c++) {
+      if ((rc = pack_one(h, h->staging + (size_t)c * DD, sh ? 1 : d.M, sh ? 0 : (long)(d.K * DD), 0, h->sys, h->nmat, 1 + c, member_mode)) != QOC_OK) return rc;
+      if (d.gradient == QOC_GRAD_EXACT)
+        if ((rc = pack_one(h, h->staging + (size_t)c * DD, sh ? 1 : d.M, sh ? 0 : (long)(d.K * DD), 1, h->sys, h->nmat, 1 + d.K + c, member_mode)) != QOC_OK) return rc;
+    }
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  {  // Xi, Xt
+    bool sh = shared_flags & QOC_SHARED_XI;
+    if ((rc = upload(Xi, (sh ? 1 : (size_t)d.M) * DD)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->xi, 1, 0, member_mode)) != QOC_OK) return rc;
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+    sh = shared_flags & QOC_SHARED_XT;
+    if ((rc = upload(Xt, (sh ? 1 : (size_t)d.M) * DD)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->xt, 1, 0, member_mode)) != QOC_OK) return rc;
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  {  // identity (initial state of qoc_total_propagator)
+    std::vector<double> I(2 * DD, 0.0);
+    for (int i = 0; i < d.D; i++) I[2 * ((size_t)i * d.D + i)] = 1.0;
+    if ((rc = upload(I.data(), DD)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, 1, 0, 0, h->ident, 1, 0, member_mode)) != QOC_OK) return rc;
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->system_set = true;
+  return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ evaluation
+static SmallParams small_params(qoc_handle* h, const double* x_dev) {
+  const qoc_desc& d = h->d;
+  SmallParams p;
+  p.D = d.D; p.N = d.N; p.K = d.K; p.M = d.M; p.R = d.R;
+  p.pack_mode = h->pack_mode; p.n_groups = h->n_groups; p.n_inner = h->n_inner; p.nmat = h->nmat;
+  p.sys_in_smem = h->sys_in_smem; p.have_P = h->have_P;
+  p.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1;
+  p.fom_exact = d.gradient == QOC_GRAD_EXACT;
+  p.dt = d.T / d.N; p.theta = d.expm_theta;
+  p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev;
+  p.storeP = h->storeP; p.storeS = h->storeS; p.fomc = h->fomc; p.gradc = h->gradc; p.out_final = nullptr;
+  return p;
+}
+static SliceParams slice_params(qoc_handle* h, const double* x_dev) {
+  const qoc_desc& d = h->d;
+  SliceParams s;
+  s.D = d.D; s.N = d.N; s.K = d.K; s.M = d.M; s.R = d.R; s.pack_mode = h->pack_mode; s.n_groups = h->n_groups;
+  s.n_inner = h->n_inner; s.nmat = h->nmat; s.dt = d.T / d.N; s.theta = d.expm_theta;
+  s.sys = h->sys; s.x = x_dev; s.storeP = nullptr; s.out_user = nullptr; s.mode = 0;
+  return s;
+}
+static int launch_chain(qoc_handle* h, const SmallParams& p, int sys, int grad, cudaStream_t st) {
+  chain_fn fn = pick_chain(h->NB, h->CPW, sys, grad);
+  if (h->smem_bytes > 48 * 1024)
+    QOC_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  fn<<<(unsigned)((h->n_groups + 3) / 4), 128, h->smem_bytes, st>>>(p);
+  return launch_check(h, "chain_kernel");
+}
+static int launch_slices(qoc_handle* h, const SliceParams& s, cudaStream_t st) {
+  long warps = (long)h->n_groups * h->d.N;
+  pick_slices(h->NB, h->CPW)<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(s);
+  return launch_check(h, "expm_slices_kernel");
+}
+
+static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int want_grad, cudaStream_t st) {
+  const qoc_desc& d = h->d;
+  int rc;
+  SmallParams p = small_params(h, x_dev);
+  const int sys = d.sys_type == QOC_UNITARY_GATE ? SYS_UNITARY : SYS_DENSITY;
+  const int grad = !want_grad ? GRAD_NONE : (d.gradient == QOC_GRAD_EXACT ? GRAD_EXACT : GRAD_FIRST);
+  if (h->have_P) {
+    SliceParams s = slice_params(h, x_dev);
+    s.storeP = h->storeP;
+    if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
+  }
+  if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
+  dim3 g1((h->NK + 1 + 255) / 256, h->red_nchunks, d.R);
+  reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->part, d.M, h->NK, h->red_chunk, h->red_nchunks);
+  if ((rc = launch_check(h, "reduce_members_pass1")) != QOC_OK) return rc;
+  dim3 g2((h->NK + 1 + 255) / 256, d.R);
+  reduce_members_pass2<<<g2, 256, 0, st>>>(h->part, fg_dev, h->NK, h->red_nchunks);
+  return launch_check(h, "reduce_members_pass2");
+}
+
+extern "C" int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream) {
+  if (!h) return QOC_EINVAL;
+  if (!x_dev || !FG_dev) { h->err = "qoc_eval_device: null pointer"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_eval_device: qoc_set_system has not been called"; return QOC_EINVAL; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  h->st.launches_last_eval = 0;
+  h->st.n_evals++;
+  if (h->path == 2) return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st);
+  return eval_small(h, x_dev, FG_dev, want_gradient, st);
+}
+
+extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
+  if (!h) return QOC_EINVAL;
+  if (!x) { h->err = "qoc_eval: null pulse"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_eval: qoc_set_system has not been called"; return QOC_EINVAL; }
+  const qoc_desc& d = h->d;
+  QOC_CUDA(h, cudaSetDevice(d.device));
+  const size_t nx = (size_t)d.R * h->NK;
+  memcpy(h->hx, x, nx * sizeof(double));
+  QOC_CUDA(h, cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  QOC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  int rc = qoc_eval_device(h, h->x, h->out, G != nullptr, h->stream);
+  if (rc != QOC_OK) return rc;
+  QOC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  const size_t row = (size_t)h->NK + 1;
+  if (G) {
+    QOC_CUDA(h, cudaMemcpyAsync(h->hout, h->out, (size_t)d.R * row * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    QOC_CUDA(h, cudaMemcpy2DAsync(h->hout, row * sizeof(double), h->out, row * sizeof(double), sizeof(double), d.R,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  }
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  QOC_CUDA(h, cudaEventElapsedTime(&h->st.gpu_ms_last_eval, h->ev0, h->ev1));
+  for (int r = 0; r < d.R; r++) {
+    if (F) F[r] = h->hout[r * row];
+    if (G) memcpy(G + (size_t)r * h->NK, h->hout + r * row + 1, sizeof(double) * h->NK);
+  }
+  return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ propagators
+static int ensure_staging(qoc_handle* h, size_t bytes) {
+  if (bytes <= h->staging_bytes) return QOC_OK;
+  if (h->staging) { cudaFree(h->staging); h->ws_bytes -= (long long)h->staging_bytes; h->staging = nullptr; h->staging_bytes = 0; }
+  QOC_CUDA(h, cudaMalloc((void**)&h->staging, bytes));
+  h->staging_bytes = bytes; h->ws_bytes += (long long)bytes; h->st.workspace_bytes = h->ws_bytes;
+  return QOC_OK;
+}
+static int upload_x(qoc_handle* h, const double* x) {
+  const size_t nx = (size_t)h->d.R * h->NK;
+  memcpy(h->hx, x, nx * sizeof(double));
+  QOC_CUDA(h, cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return QOC_OK;
+}
+
+extern "C" int qoc_total_propagator(qoc_handle* h, const double* x, double* U) {
+  if (!h) return QOC_EINVAL;
+  if (!x || !U) { h->err = "qoc_total_propagator: null pointer"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_total_propagator: qoc_set_system has not been called"; return QOC_EINVAL; }
+  const qoc_desc& d = h->d;
+  QOC_CUDA(h, cudaSetDevice(d.device));
+  h->st.launches_last_eval = 0;
+  int rc;
+  if ((rc = upload_x(h, x)) != QOC_OK) return rc;
+  const size_t bytes = (size_t)d.R * d.M * d.D * d.D * sizeof(double2);
+  if ((rc = ensure_staging(h, bytes)) != QOC_OK) return rc;
+  if (h->path == 2) {
+    if ((rc = big_total_propagator(h->big, h->x, h->staging, h->stream, h->err, h->st)) != QOC_OK) return rc;
+  } else {
+    SmallParams p = small_params(h, h->x);
+    p.xi = h->ident; p.out_final = h->staging; p.have_P = 0; p.fom_exact = 0;
+    if ((rc = launch_chain(h, p, SYS_UNITARY, GRAD_NONE, h->stream)) != QOC_OK) return rc;
+  }
+  QOC_CUDA(h, cudaMemcpyAsync(U, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QOC_OK;
+}
+
+extern "C" int qoc_propagators(qoc_handle* h, const double* x, double* out, int mode) {
+  if (!h) return QOC_EINVAL;
+  if (!x || !out || mode < 0 || mode > 2) { h->err = "qoc_propagators: bad argument"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_propagators: qoc_set_system has not been called"; return QOC_EINVAL; }
+  const qoc_desc& d = h->d;
+  QOC_CUDA(h, cudaSetDevice(d.device));
+  h->st.launches_last_eval = 0;
+  int rc;
+  if ((rc = upload_x(h, x)) != QOC_OK) return rc;
+  const size_t bytes = (size_t)d.R * d.M * d.N * d.D * d.D * sizeof(double2);
+  if ((rc = ensure_staging(h, bytes)) != QOC_OK) return rc;
+  if (h->path == 2) {
+    if ((rc = big_propagators(h->big, h->x, h->staging, mode, h->stream, h->err, h->st)) != QOC_OK) return rc;
+  } else {
+    SliceParams s = slice_params(h, h->x);
+    s.out_user = h->staging; s.mode = mode;
+    if ((rc = launch_slices(h, s, h->stream)) != QOC_OK) return rc;
+  }
+  QOC_CUDA(h, cudaMemcpyAsync(out, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return QOC_OK;
+}
+
+extern "C" int qoc_get_stats(qoc_handle* h, qoc_stats* out) {
+  if (!h || !out) return QOC_EINVAL;
+  h->st.workspace_bytes = h->ws_bytes + (h->big ? big_workspace(h->big) : 0);
+  *out = h->st;
+  return QOC_OK;
+}

@@ -1,0 +1,121 @@
+"""GrapeEvaluator: one persistent device handle = the reference's work arrays (init_GRAPE,
+/root/reference/src/grape_tools.jl:4-16) + the body of the Optim.only_fg! closure
+(/root/reference/src/solve.jl:75-100, :164-196), executed by libqocgrape.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _colmajor(mats, D):
+    """Stack of matrices -> contiguous buffer of column-major complex128 D x D blocks."""
+    a = np.asarray(mats, dtype=np.complex128)
+    if a.shape[-2:] != (D, D):
+        raise ValueError(f"expected matrices of shape ({D},{D}), got {a.shape}")
+    return np.ascontiguousarray(np.swapaxes(a, -1, -2))
+
+
+class GrapeEvaluator:
+    """members: list of (A, B, Xi, Xt) tuples (one per ensemble member; a plain Problem is one member).
+    x has shape (K, N) like the reference's control_array, or (R, K, N) for a multi-start batch."""
+
+    def __init__(self, members, T, n_slices, sys_type, wts=None, gradient="first_order",
+                 convention="inplace", n_pulses=1, device=0, expm_theta=0.0):
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        M = len(members)
+        A0, B0, Xi0, Xt0 = members[0]
+        D = np.asarray(A0).shape[0]
+        K = len(B0)
+        self.D, self.K, self.N, self.M, self.R = D, K, int(n_slices), M, int(n_pulses)
+        code = sys_type if isinstance(sys_type, int) else sys_type.code
+        desc = _lib.QocDesc(sys_type=code, D=D, K=K, N=self.N, M=M, R=self.R, T=float(T),
+                            gradient={"first_order": _lib.GRAD_FIRST_ORDER, "exact": _lib.GRAD_EXACT}[gradient],
+                            convention={"inplace": _lib.REF_INPLACE, "static": _lib.REF_STATIC}[convention],
+                            device=int(device), expm_theta=float(expm_theta), flags=0)
+        rc = self._lib.qoc_create(C.byref(self._h), C.byref(desc))
+        if rc != _lib.QOC_OK:
+            msg = self._lib.qoc_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise _lib.QocError(rc, msg)
+        A = _colmajor([m[0] for m in members], D)
+        B = _colmajor([[b for b in m[1]] for m in members], D) if K else np.zeros(1, dtype=np.complex128)
+        Xi = _colmajor([m[2] for m in members], D)
+        Xt = _colmajor([m[3] for m in members], D)
+        w = None if wts is None else np.ascontiguousarray(np.asarray(wts, dtype=np.float64))
+        if w is not None and w.shape != (M,):
+            raise ValueError("wts must have one weight per member")
+        self._check(self._lib.qoc_set_system(self._h, A.ctypes.data, B.ctypes.data, Xi.ctypes.data, Xt.ctypes.data,
+                                             None if w is None else w.ctypes.data, 0))
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc):
+        if rc != _lib.QOC_OK:
+            raise _lib.QocError(rc, self._lib.qoc_last_error(self._h).decode())
+
+    def _pack_x(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 2:
+            x = x[None]
+        if x.shape != (self.R, self.K, self.N):
+            raise ValueError(f"pulse must have shape ({self.R},{self.K},{self.N}) or ({self.K},{self.N}), got {x.shape}")
+        return np.ascontiguousarray(np.swapaxes(x, 1, 2))      # [R][N][K] == Julia K x N column-major
+
+    # ------------------------------------------------------------------ API
+    def eval(self, x, want_grad=True):
+        """Returns (F, G): floats/arrays for R == 1 and 2-D x, else F[R], G[R, K, N]."""
+        single = np.asarray(x).ndim == 2
+        xb = self._pack_x(x)
+        F = np.empty(self.R)
+        G = np.empty((self.R, self.N, self.K)) if want_grad else None
+        self._check(self._lib.qoc_eval(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
+        Gk = None if G is None else np.swapaxes(G, 1, 2)
+        if single:
+            return float(F[0]), (None if Gk is None else np.ascontiguousarray(Gk[0]))
+        return F, Gk
+
+    def eval_device(self, x_dev_ptr, fg_dev_ptr, want_grad=True, stream=None):
+        """Asynchronous evaluation on device pointers (ints): x [R][N][K], FG [R][1 + N*K]."""
+        self._check(self._lib.qoc_eval_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
+
+    def total_propagator(self, x):
+        """pw_evolve with U0 = I (src/timeevolution.jl:28-39): U[R, M, D, D] (squeezed for R = M = 1)."""
+        xb = self._pack_x(x)
+        U = np.empty((self.R, self.M, self.D, self.D), dtype=np.complex128)
+        self._check(self._lib.qoc_total_propagator(self._h, xb.ctypes.data, U.ctypes.data))
+        U = np.swapaxes(U, -1, -2)
+        return U[0, 0].copy() if (self.R == 1 and self.M == 1) else U
+
+    def propagators(self, x, what="propagator"):
+        """pw_prop_save! / pw_ham_save! / pw_gen_save!: out[R, M, N, D, D] (squeezed for R = M = 1)."""
+        mode = {"propagator": 0, "hamiltonian": 1, "generator": 2}[what]
+        xb = self._pack_x(x)
+        P = np.empty((self.R, self.M, self.N, self.D, self.D), dtype=np.complex128)
+        self._check(self._lib.qoc_propagators(self._h, xb.ctypes.data, P.ctypes.data, mode))
+        P = np.swapaxes(P, -1, -2)
+        return P[0, 0].copy() if (self.R == 1 and self.M == 1) else P
+
+    def stats(self):
+        st = _lib.QocStats()
+        self._check(self._lib.qoc_get_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
+    def close(self):
+        if self._h:
+            self._lib.qoc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
