@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — GRAPE fidelity+gradient evaluations/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4|cfg1|cfg2|cfg3|cfg5] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One "step" = one evaluation of the (F, G, x) closure (solve.jl:75-100 / :164-196) for the whole workload: all
+ensemble members weighted and summed (and, for N > 1, one all-reduce of [F|G] over NCCL).  Default workload:
+BASELINE.json configs[3], the 4096-member robust ensemble (the config the 1/2/4/8-GPU metric is quoted on); its
+members are sharded over the ranks (strong scaling: total work fixed).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "GRAPE fidelity+gradient evals/sec"
+UNIT = "evals/s"
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak.json")
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
+
+
+def build_config(name):
+    import quoptimalcontrol_jl_b200 as qoc
+    c = qoc.configs
+    if name == "cfg4":
+        return c.config4()
+    if name == "cfg1":
+        return c.config1()
+    if name == "cfg2":
+        return c.config2()
+    if name == "cfg3":
+        return c.config3()
+    if name == "cfg5":
+        return c.config5()
+    raise SystemExit(f"unknown config {name}")
+
+
+DEFAULT_PULSES = {"cfg4": 1, "cfg5": 1, "cfg1": 65536, "cfg2": 4096, "cfg3": 1024}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [r for _, r in self.rows]
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [s.strip() for s in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, cfg, rank):
+    """--impl reference: the reference's own CPU implementation of the path, restated in C (oracle/grape_oracle.c,
+    Julia being unavailable), all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import c_oracle, grape_oracle
+    members, wts = cfg["members"], cfg["wts"]
+    M = len(members)
+    D = members[0][0].shape[0]
+    threads = os.cpu_count() or 1
+    if D > 16:
+        kind_fn = "numpy"
+    else:
+        kind_fn = "c"
+    # bounded sample: members for ensembles, slices for single long chains (cost is linear in both)
+    if M > 1:
+        ms = min(M, max(threads, 64))
+        sample_members, sample_w, x, N = members[:ms], (wts[:ms] if wts is not None else None), cfg["x"], cfg["N"]
+        scale = M / ms
+        sample = f"{ms} of {M} members (all {cfg['N']} slices), scaled x{scale:g}"
+    else:
+        ns = min(cfg["N"], 200 if D <= 16 else 8)
+        sample_members, sample_w, x, N = members, wts, cfg["x"][:, :ns], ns
+        scale = cfg["N"] / ns
+        sample = f"{ns} of {cfg['N']} slices, scaled x{scale:g}"
+    T = cfg["T"] * N / cfg["N"]
+
+    def step():
+        if kind_fn == "c":
+            if cfg["gradient"] == "exact":
+                return grape_oracle.ensemble_exact(sample_members, sample_w if sample_w is not None else [1.0], x, T, cfg["sys_type"])
+            return c_oracle.eval_ensemble(sample_members, sample_w, x, T, cfg["sys_type"], 0, threads)
+        return grape_oracle.ensemble_fom_and_gradient(sample_members, sample_w if sample_w is not None else [1.0], x, T, cfg["sys_type"])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = 1.0 / (dt * scale)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": cfg["name"], "gradient": cfg["gradient"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind_fn == "c" and M > 1 else (threads if kind_fn == "numpy" else 1),
+                             "kind": "port", "sample": sample + ("; C restatement + OpenMP over members" if kind_fn == "c" else "; numpy/OpenBLAS restatement")},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="cfg4")
+    ap.add_argument("--pulses", type=int, default=0, help="multi-start pulses per step (0 = config default)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = build_config(args.config)
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import quoptimalcontrol_jl_b200 as qoc
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    members, wts = cfg["members"], cfg["wts"]
+    M = len(members)
+    K, N = cfg["x"].shape
+    R = args.pulses or DEFAULT_PULSES[args.config]
+    sharded = M > 1
+    if sharded:   # ensemble members sharded over ranks, one all-reduce of [F|G] per evaluation
+        lo, hi = rank * M // world, (rank + 1) * M // world
+        my_members, my_wts, my_R = members[lo:hi], wts[lo:hi], R
+        parallelism = f"ensemble-sharded x{world} + allreduce" if world > 1 else "single GPU"
+    else:         # M = 1: replicas over independent multi-start pulses, no collective
+        my_members, my_wts, my_R = members, wts, R
+        parallelism = f"multi-start replicas x{world}, no collective" if world > 1 else "single GPU"
+    rng = np.random.default_rng(1234 + (0 if sharded else rank))
+    xs = np.concatenate([cfg["x"][None], rng.uniform(-1, 1, (my_R - 1, K, N))]) if my_R > 1 else cfg["x"][None]
+
+    ev = qoc.GrapeEvaluator(my_members, cfg["T"], N, cfg["sys_type"], wts=my_wts, gradient=cfg["gradient"],
+                            n_pulses=my_R, device=local_rank)
+    x_host = torch.from_numpy(np.ascontiguousarray(np.swapaxes(xs, 1, 2))).pin_memory()     # [R][N][K]
+    x_dev = x_host.to(dev)
+    fg_dev = torch.zeros((my_R, N * K + 1), dtype=torch.float64, device=dev)
+    fg_host = torch.zeros((my_R, N * K + 1), dtype=torch.float64).pin_memory()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    def step_device():
+        ev.eval_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
+        if world > 1 and sharded:
+            dist.all_reduce(fg_dev)
+
+    def step_e2e():
+        if world == 1:
+            return ev.eval(xs if my_R > 1 else xs[0])            # C-ABI call with host buffers (H2D + kernels + D2H)
+        x_dev.copy_(x_host, non_blocking=True)
+        step_device()
+        fg_host.copy_(fg_dev, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ev.stats()                                    # reset the kernel-event ring
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    ms = e0.elapsed_time(e1) / args.steps
+    st = ev.stats()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    evals_per_step = R if sharded else R * world
+    value = evals_per_step / (ms * 1e-3)
+
+    # ---- end-to-end timing through the public API (host buffers, copies inside the timed region) ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": evals_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(my_R * N * K * 8),
+           "d2h_bytes_per_step": int(my_R * (N * K + 1) * 8)}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    flops_total = qoc.configs.alg_flops(cfg) * R                    # algorithmic FLOPs of one step, whole job
+    flops_rank = flops_total / world if sharded else flops_total    # per launch of this rank's kernel
+    peak, peak_src = 37.1, "fallback constant (tools/microbench/fp64_pipes.cu DMMA burst)"
+    if os.path.exists(FP64_PEAK_FILE):
+        with open(FP64_PEAK_FILE) as f:
+            pj = json.load(f)
+        peak, peak_src = float(pj["fp64_dmma_tflops"]), pj["source"]
+    k_ms = st["main_kernel_ms_avg"] or ms
+    achieved = flops_rank / (k_ms * 1e-3) / 1e12
+    traffic = None
+    if os.path.exists(TRAFFIC_FILE):
+        with open(TRAFFIC_FILE) as f:
+            traffic = json.load(f).get(args.config)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "chain_kernel (FP64 DMMA pipe)", "kernel_ms": k_ms,
+                "kernel_samples": st["main_kernel_samples"], "alg_flops_per_launch": flops_rank,
+                "peak_source": peak_src + " — MEASURED_PEAKS.json has no FP64 entry"}
+
+    # ---- CPU baseline (reference restated in C, all host threads, bounded sample) + parity gate ----
+    cpu_baseline, parity = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import c_oracle, grape_oracle
+        threads = os.cpu_count() or 1
+        D = members[0][0].shape[0]
+        if M > 1:
+            ms_n = min(M, max(2 * threads, 64))
+            sm, sw = members[:ms_n], wts[:ms_n]
+            t0 = time.perf_counter()
+            Fo, Go = c_oracle.eval_ensemble(sm, sw, cfg["x"], cfg["T"], cfg["sys_type"], 0, threads)
+            tc = time.perf_counter() - t0
+            cpu_baseline = {"value": 1.0 / (tc * M / ms_n), "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": f"{ms_n} of {M} members, all {N} slices, C restatement of the reference loop order with OpenMP over members (the Julia reference is serial); scaled x{M / ms_n:g}"}
+            with qoc.GrapeEvaluator(sm, cfg["T"], N, cfg["sys_type"], wts=sw, gradient=cfg["gradient"], device=local_rank) as ev2:
+                Fg, Gg = ev2.eval(cfg["x"])
+        else:
+            ns = min(N, 100)
+            xsmp = cfg["x"][:, :ns]
+            Ts = cfg["T"] * ns / N
+            t0 = time.perf_counter()
+            if cfg["gradient"] == "exact":
+                Fo, Go = grape_oracle.exact_fom_and_gradient(*members[0][:2], xsmp, Ts, *members[0][2:], cfg["sys_type"])
+                how = "numpy restatement of the ADGRAPE functional with augmented-matrix derivatives"
+            else:
+                Fo, Go = c_oracle.eval_ensemble(members, None, xsmp, Ts, cfg["sys_type"], 0, 1)
+                how = "C restatement of the reference loop order, 1 thread (the reference is serial)"
+            tc = time.perf_counter() - t0
+            cpu_baseline = {"value": 1.0 / (tc * N / ns), "unit": UNIT, "cores": 1, "kind": "port",
+                            "sample": f"{ns} of {N} slices, {how}; scaled x{N / ns:g}"}
+            with qoc.GrapeEvaluator(members, Ts, ns, cfg["sys_type"], gradient=cfg["gradient"], device=local_rank) as ev2:
+                Fg, Gg = ev2.eval(xsmp)
+        parity = {"fom_rel_err": abs(Fg - Fo) / max(1.0, abs(Fo)),
+                  "grad_rel_err_inf": float(np.max(np.abs(Gg - Go)) / max(np.max(np.abs(Go)), 1e-300)),
+                  "checked_on": cpu_baseline["sample"].split(",")[0], "tolerance": "1e-10 fom / 1e-8 gradient"}
+
+    D = members[0][0].shape[0]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["name"], "D": D, "K": K, "N": N, "M": M, "pulses_per_step": evals_per_step,
+                       "gradient": cfg["gradient"], "parallelism": parallelism,
+                       "l2": "no flush: each step streams its 2 x %.2f GB propagator/state stores (>> 126 MB L2)" % (st["workspace_bytes"] / 2e9)},
+            "e2e": e2e, "gpu_launches": int(st["launches_last_eval"]) * args.steps, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,9 @@ typedef struct qoc_stats {
   float gpu_ms_last_eval;     /* device time of the most recent qoc_eval (CUDA events), 0 for eval_device */
   long long workspace_bytes;  /* device memory held */
   int path;                   /* 1 = warp-resident DMMA (D <= 16), 2 = tiled DMMA GEMM (D > 16) */
+  float main_kernel_ms_avg;   /* mean device time of the dominant kernel over the evaluations since the previous
+                                 qoc_get_stats call (CUDA events on the launching stream, at most 64 samples) */
+  int main_kernel_samples;
 } qoc_stats;
 
 const char* qoc_version(void);
@@ -99,8 +102,8 @@ int qoc_set_system(qoc_handle* h, const double* A, const double* B, const double
  *   x [R][N*K] host;  F [R] or NULL;  G [R][N*K] or NULL (value-only evaluation skips the backward sweep). */
 int qoc_eval(qoc_handle* h, const double* x, double* F, double* G);
 
-/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the handle's
- * stream): x_dev [R][N*K];  FG_dev [R][1 + N*K] with F first, then G.  Lets one-process-per-GPU callers
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the CUDA default
+ * stream, as everywhere in the CUDA runtime): x_dev [R][N*K];  FG_dev [R][1 + N*K] with F first, then G.  Lets one-process-per-GPU callers
  * all-reduce FG_dev (NCCL) without a host round trip. */
 int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);
 

@@ -23,7 +23,8 @@ class QocDesc(C.Structure):
 
 class QocStats(C.Structure):
     _fields_ = [("n_evals", C.c_longlong), ("n_launches", C.c_longlong), ("launches_last_eval", C.c_int),
-                ("gpu_ms_last_eval", C.c_float), ("workspace_bytes", C.c_longlong), ("path", C.c_int)]
+                ("gpu_ms_last_eval", C.c_float), ("workspace_bytes", C.c_longlong), ("path", C.c_int),
+                ("main_kernel_ms_avg", C.c_float), ("main_kernel_samples", C.c_int)]
 
 
 class QocError(RuntimeError):

@@ -19,6 +19,9 @@ struct qoc_handle {
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static constexpr int KRING = 64;           // event pairs around the dominant kernel of recent evaluations
+  cudaEvent_t ek0[KRING] = {}, ek1[KRING] = {};
+  int kring_count = 0;
   // derived small-path geometry
   int path = 0, NB = 1, CPW = 1, pack_mode = 0, n_groups = 0, n_inner = 0, n_sysgroups = 0, nmat = 0;
   int have_P = 0, sys_in_smem = 0, smem_bytes = 0;
@@ -115,6 +118,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
   CRC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CRC(cudaEventCreate(&h->ev0));
   CRC(cudaEventCreate(&h->ev1));
+  for (int i = 0; i < qoc_handle::KRING; i++) { CRC(cudaEventCreate(&h->ek0[i])); CRC(cudaEventCreate(&h->ek1[i])); }
 
   const size_t DD = (size_t)d.D * d.D;
   if (d.D <= 16) {
@@ -174,6 +178,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->hout) cudaFreeHost(h->hout);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < qoc_handle::KRING; i++) { if (h->ek0[i]) cudaEventDestroy(h->ek0[i]); if (h->ek1[i]) cudaEventDestroy(h->ek1[i]); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return QOC_OK;
@@ -296,7 +301,11 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
     s.storeP = h->storeP;
     if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
   }
+  const int slot = h->kring_count % qoc_handle::KRING;
+  QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
+  QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st));
+  h->kring_count++;
   dim3 g1((h->NK + 1 + 255) / 256, h->red_nchunks, d.R);
   reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->part, d.M, h->NK, h->red_chunk, h->red_nchunks);
   if ((rc = launch_check(h, "reduce_members_pass1")) != QOC_OK) return rc;
@@ -305,16 +314,19 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   return launch_check(h, "reduce_members_pass2");
 }
 
+static int eval_device_on(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, cudaStream_t st) {
+  h->st.launches_last_eval = 0;
+  h->st.n_evals++;
+  if (h->path == 2) return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st);
+  return eval_small(h, x_dev, FG_dev, want_gradient, st);
+}
+
 extern "C" int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream) {
   if (!h) return QOC_EINVAL;
   if (!x_dev || !FG_dev) { h->err = "qoc_eval_device: null pointer"; return QOC_EINVAL; }
   if (!h->system_set) { h->err = "qoc_eval_device: qoc_set_system has not been called"; return QOC_EINVAL; }
   QOC_CUDA(h, cudaSetDevice(h->d.device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  h->st.launches_last_eval = 0;
-  h->st.n_evals++;
-  if (h->path == 2) return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st);
-  return eval_small(h, x_dev, FG_dev, want_gradient, st);
+  return eval_device_on(h, x_dev, FG_dev, want_gradient, (cudaStream_t)stream);   // NULL = CUDA default stream
 }
 
 extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
@@ -327,7 +339,7 @@ extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
   memcpy(h->hx, x, nx * sizeof(double));
   QOC_CUDA(h, cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   QOC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  int rc = qoc_eval_device(h, h->x, h->out, G != nullptr, h->stream);
+  int rc = eval_device_on(h, h->x, h->out, G != nullptr, h->stream);
   if (rc != QOC_OK) return rc;
   QOC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   const size_t row = (size_t)h->NK + 1;
@@ -410,6 +422,17 @@ extern "C" int qoc_propagators(qoc_handle* h, const double* x, double* out, int 
 extern "C" int qoc_get_stats(qoc_handle* h, qoc_stats* out) {
   if (!h || !out) return QOC_EINVAL;
   h->st.workspace_bytes = h->ws_bytes + (h->big ? big_workspace(h->big) : 0);
+  {  // average over the event pairs recorded since the previous qoc_get_stats (at most KRING)
+    int n = h->kring_count < qoc_handle::KRING ? h->kring_count : qoc_handle::KRING;
+    double sum = 0; int got = 0;
+    for (int i = 0; i < n; i++) {
+      float ms = 0;
+      if (cudaEventSynchronize(h->ek1[i]) == cudaSuccess && cudaEventElapsedTime(&ms, h->ek0[i], h->ek1[i]) == cudaSuccess) { sum += ms; got++; }
+    }
+    h->st.main_kernel_ms_avg = got ? (float)(sum / got) : 0.f;
+    h->st.main_kernel_samples = got;
+    h->kring_count = 0;
+  }
   *out = h->st;
   return QOC_OK;
 }
