@@ -1,5 +1,5 @@
 """The five BASELINE.json workloads as synthetic Hamiltonians / pulses, plus scaled-down
-variants for parity tests.  numpy only; seeds fixed so every consumer (tests, bench, oracle) sees identical bits."""
+variants for parity tests.  numpy only; seeds fixed so every consumer (tests, bench, CPU checker) sees identical bits."""
 from __future__ import annotations
 
 from functools import reduce

@@ -1,0 +1,55 @@
+"""Host-side logic that needs no GPU: problem types, ensemble expansion, BASELINE config builders."""
+import numpy as np
+
+import quoptimalcontrol_jl_b200 as qoc
+from oracle import grape_oracle as orc
+
+
+def test_problem_types_and_old_names():
+    Z = np.zeros((2, 2), dtype=complex)
+    p = qoc.ClosedStateTransfer(B=[Z], A=Z, Xi=Z, Xt=Z, T=1.0, n_controls=1, guess=np.zeros((1, 3)))
+    assert isinstance(p.sys_type, qoc.StateTransfer) and p.sys_type.code == orc.STATE_TRANSFER
+    assert isinstance(qoc.UnitarySynthesis(B=[Z], A=Z, Xi=Z, Xt=Z, T=1.0, n_controls=1, guess=None).sys_type, qoc.UnitaryGate)
+    assert qoc.OpenSystemCoherenceTransfer(B=[Z], A=Z, Xi=Z, Xt=Z, T=1.0, n_controls=1, guess=None).sys_type.code == orc.COHERENCE_TRANSFER
+
+
+def test_init_ensemble_follows_reference_fixture():
+    """test/setup_tests.jl:31-49: detuning sweep A_gens(k) = (k - 2.5)/2.5 * Sz * 5, alternating targets."""
+    Sz = np.diag([0.5, -0.5]).astype(complex)
+    r0, r1 = np.diag([1, 0]).astype(complex), np.diag([0, 1]).astype(complex)
+    prob = qoc.Problem(B=[Sz], A=Sz, Xi=r0, Xt=r1, T=5.0, n_controls=1, guess=np.zeros((1, 25)), sys_type=qoc.StateTransfer())
+    ens = qoc.EnsembleProblem(prob=prob, n_ens=5, A_g=lambda k: (k - 2.5) / 2.5 * Sz * 5, B_g=lambda k: [Sz],
+                              XiG=lambda k: r0, XtG=lambda k: r1 if k % 2 else r0, wts=np.ones(5) / 5)
+    ms = qoc.init_ensemble(ens)
+    assert len(ms) == 5
+    assert np.allclose(ms[0].A, -3.0 * Sz) and np.allclose(ms[4].A, 5.0 * Sz)
+    assert np.allclose(ms[0].Xt, r1) and np.allclose(ms[1].Xt, r0)
+    assert ms[2].T == 5.0 and prob.A is Sz       # template untouched
+
+
+def test_baseline_config_shapes_and_flops():
+    c = qoc.configs
+    c4 = c.config4(N=4, grid=2)
+    assert len(c4["members"]) == 4 and c4["members"][0][0].shape == (8, 8) and len(c4["members"][0][1]) == 6
+    assert abs(sum(c4["wts"]) - 1) < 1e-15
+    full = dict(c4, members=[c4["members"][0]] * 4096, N=500)
+    assert c.alg_flops(full) == 4096 * 500 * 4096 * 6          # 50.3 GFLOP
+    c5 = c.config5(N=2, n=8)
+    assert c5["members"][0][0].shape == (256, 256) and len(c5["members"][0][1]) == 16
+    assert c.alg_flops(dict(c5, N=2000)) == 2000 * 8 * 256 ** 3 * 9   # 2.416 TFLOP
+    c3 = c.config3(N=3)
+    A = c3["members"][0][0]
+    # trace preservation of the Liouvillian convention P = exp(-i dt A): vec(I)' A = 0
+    vI = np.eye(4).reshape(-1, order="F")
+    assert np.max(np.abs(vI @ A)) < 1e-14
+    c2 = c.config2(N=10)
+    assert c2["gradient"] == "exact" and c2["members"][0][3].shape == (4, 4)
+
+
+def test_shard_bounds_cover_everything():
+    for M in (1, 5, 64, 4096):
+        for W in (1, 2, 3, 8):
+            parts = [qoc.shard_bounds(M, r, W) for r in range(W)]
+            assert parts[0][0] == 0 and parts[-1][1] == M
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
