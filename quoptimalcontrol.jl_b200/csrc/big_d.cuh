@@ -1,18 +1,520 @@
-// Large-dimension path (D > 16): tiled DMMA complex GEMM pipeline.  Placeholder until the tiled kernels land:
-// every entry returns QOC_EUNSUPPORTED (there is no CPU fallback).
+// Large-dimension GRAPE path (D > 16): every product is a batched DMMA complex GEMM (zgemm_dmma.cuh).
+// The slice dependence of the forward/backward sweeps is broken into Cn chunks that advance in lock step
+// (batch = Cn GEMMs per launch), after the chunk boundary states have been obtained from chunk-total propagators:
+//   phase 1  P_t = exp(-i dt H_t) for all slices  (assemble, 1-norm -> scaling s, T8 in 3 fused GEMMs, s squarings)
+//            -- pw_prop_save!, /root/reference/src/timeevolution.jl:98-110
+//   phase 2  T_c = product of the chunk's propagators (Cn independent chains of L-1 products)
+//   phase 3  boundary states S[start_c], costates C[start_c] through the T_c (short sequential chains)
+//   phase 4  forward / backward sweeps inside all chunks concurrently, storing S_t and C_t
+//            -- evolve_func!, /root/reference/src/GRAPE.jl:53-75, 216-251
+//   phase 5  W_t = S_t C_t' (- C_t' S_t for density types) for all slices, then K trace-dots per slice over the
+//            non-zeros of B_c  -- grad_func!, /root/reference/src/GRAPE.jl:261-287;  fom_func, cost_functions.jl:99-111
+// First-order gradient only (the exact mode of this path is not implemented: QOC_EUNSUPPORTED).
 #pragma once
 #include <string>
+#include <vector>
+#include <algorithm>
+#include <cmath>
 #include "../../include/qocgrape.h"
+#include "zgemm_dmma.cuh"
 
 namespace qoc {
-struct BigState { int dummy; };
-static inline int big_create(BigState**, const qoc_desc& d, std::string& err, long long&) {
-  err = "D = " + std::to_string(d.D) + " > 16 is not implemented by the CUDA path yet"; return QOC_EUNSUPPORTED;
+
+constexpr double BT8_X1 = 0.10836465678522780852, BT8_X2 = 0.027091164196306952131, BT8_X3 = 0.66666666666666666667,
+                 BT8_X4 = 0.54676145797072405251, BT8_X5 = 0.16112557339541759283, BT8_X6 = 0.014090917158378207731,
+                 BT8_X7 = 0.033792797010870504141, BT8_Y2 = 0.13549236135285063166;
+
+// ---------------------------------------------------------------------------------------------- small kernels
+// out_t[e] = f(A[e] + sum_j x[t][j] B_j[e]); mode 0/2: -i*dt*H (generator), mode 1: H.  One thread per element,
+// looping over a range of slices so A and B_j are read once.
+__global__ void big_assemble_kernel(const double2* __restrict__ A, const double2* __restrict__ B, const double* __restrict__ x,
+                                    double2* __restrict__ out, int DD, int K, int N, int slices_per_block, double dt, int mode) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= DD) return;
+  int t0 = blockIdx.y * slices_per_block, t1 = min(N, t0 + slices_per_block);
+  double2 a = A[e];
+  for (int t = t0; t < t1; t++) {
+    double hr = a.x, hi = a.y;
+    for (int j = 0; j < K; j++) {
+      double xj = __ldg(x + (size_t)t * K + j);
+      double2 bj = __ldg(B + (size_t)j * DD + e);
+      hr = fma(xj, bj.x, hr); hi = fma(xj, bj.y, hi);
+    }
+    out[(size_t)t * DD + e] = mode == 1 ? make_double2(hr, hi) : make_double2(dt * hi, -dt * hr);
+  }
 }
-static inline void big_destroy(BigState*) {}
-static inline long long big_workspace(BigState*) { return 0; }
-static inline int big_set_system(BigState*, const double*, const double*, const double*, const double*, int, std::string&) { return QOC_EUNSUPPORTED; }
-static inline int big_eval(BigState*, const double*, double*, int, const double*, cudaStream_t, std::string&, qoc_stats&) { return QOC_EUNSUPPORTED; }
-static inline int big_total_propagator(BigState*, const double*, double2*, cudaStream_t, std::string&, qoc_stats&) { return QOC_EUNSUPPORTED; }
-static inline int big_propagators(BigState*, const double*, double2*, int, cudaStream_t, std::string&, qoc_stats&) { return QOC_EUNSUPPORTED; }
+// per-slice 1-norm bound (column sums of |re|+|im|); one block per slice, one warp per column round-robin.
+__global__ void big_norm_kernel(const double2* __restrict__ G, int D, float* __restrict__ norms) {
+  __shared__ float wmax[32];
+  const double2* g = G + (size_t)blockIdx.x * D * D;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float best = 0.f;
+  for (int col = warp; col < D; col += nw) {
+    float s = 0.f;
+    for (int r = lane; r < D; r += 32) { double2 v = g[(size_t)col * D + r]; s += (float)(fabs(v.x) + fabs(v.y)); }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    best = fmaxf(best, s);
+  }
+  if (lane == 0) wmax[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) { float m = 0.f; for (int i = 0; i < nw; i++) m = fmaxf(m, wmax[i]); norms[blockIdx.x] = m * 1.000001f; }
+}
+__global__ void big_scale_power_kernel(const float* __restrict__ norms, int N, float theta, int* __restrict__ s_out) {
+  __shared__ float sm[256];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, norms[i]);
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]); __syncthreads(); }
+  if (threadIdx.x == 0) { int s = 0; if (sm[0] > theta) { s = ilogbf(sm[0] / theta) + 1; if (s > 60) s = 60; } *s_out = s; }
+}
+// tau = sum conj(X) .* Y over D*D elements (one block, fixed-order tree); then the figure of merit.
+//   unitary (reference): X = S_N, Y = Xt, fom = Re(tau^2);   density: X = Xt, Y = S_N, fom = 1 - |tau|^2/D^2
+__global__ void big_fom_kernel(const double2* __restrict__ X, const double2* __restrict__ Y, int DD, int unitary, double invD2,
+                               double* __restrict__ tau_fom /* [3]: tau_re, tau_im, fom */) {
+  __shared__ double sr[256], si[256];
+  double pr = 0, pi = 0;
+  for (int e = threadIdx.x; e < DD; e += blockDim.x) {
+    double2 a = X[e], b = Y[e];
+    pr += a.x * b.x + a.y * b.y; pi += a.x * b.y - a.y * b.x;
+  }
+  sr[threadIdx.x] = pr; si[threadIdx.x] = pi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) { if (threadIdx.x < o) { sr[threadIdx.x] += sr[threadIdx.x + o]; si[threadIdx.x] += si[threadIdx.x + o]; } __syncthreads(); }
+  if (threadIdx.x == 0) {
+    tau_fom[0] = sr[0]; tau_fom[1] = si[0];
+    tau_fom[2] = unitary ? sr[0] * sr[0] - si[0] * si[0] : 1.0 - (sr[0] * sr[0] + si[0] * si[0]) * invD2;
+  }
+}
+// g[t][c] = Re( f * sum_nz B_c[a][b] * W_t[b][a] ), one block per (slice, control) over the control's non-zeros.
+//   f = i*dt (density) or 2*(+-i dt)*tau (unitary, tau read from tau_fom)
+struct BigTraceParams {
+  const double2* W; int D, K, N; const int* coo_ptr; const int2* coo_idx; const double2* coo_val;
+  const double* tau_fom; int unitary; double dt; int sign_static; double* g /* [N][K] */;
+};
+__global__ void big_trace_kernel(const BigTraceParams p) {
+  __shared__ double sr[128];
+  int t = blockIdx.x, c = blockIdx.y;
+  double fr, fi;
+  if (p.unitary) { double sg = 2.0 * p.sign_static * p.dt; fr = -sg * p.tau_fom[1]; fi = sg * p.tau_fom[0]; }
+  else { fr = 0.0; fi = p.dt; }
+  const double2* W = p.W + (size_t)t * p.D * p.D;
+  double acc = 0;
+  for (int e = p.coo_ptr[c] + threadIdx.x; e < p.coo_ptr[c + 1]; e += blockDim.x) {
+    int2 ab = p.coo_idx[e]; double2 bv = p.coo_val[e];
+    double2 w = W[(size_t)ab.x * p.D + ab.y];            // W[b][a] at column a = ab.x, row b = ab.y
+    double zr = bv.x * w.x - bv.y * w.y, zi = bv.x * w.y + bv.y * w.x;
+    acc += fr * zr - fi * zi;
+  }
+  sr[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) { if (threadIdx.x < o) sr[threadIdx.x] += sr[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) p.g[(size_t)t * p.K + c] = sr[0];
+}
+// FG[0] += w * fom; FG[1 + i] += w * g[i]   (stream order makes the member sum deterministic: k ascending)
+__global__ void big_accumulate_kernel(double* __restrict__ FG, const double* __restrict__ tau_fom, const double* __restrict__ g,
+                                      const double* __restrict__ wts, int k, int NK, int first, int want_grad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > NK) return;
+  if (i > 0 && !want_grad) return;
+  double w = wts[k];
+  double v = i == 0 ? tau_fom[2] : g[i - 1];
+  FG[i] = first ? w * v : FG[i] + w * v;
+}
+
+// ---------------------------------------------------------------------------------------------- host state
+struct BigState {
+  qoc_desc d{};
+  int Dp = 0, Cn = 1, Lmax = 1, unitary = 0;
+  size_t DD = 0;
+  std::vector<int> start, len;
+  cudaStream_t sA = nullptr, sB = nullptr;
+  cudaEvent_t evFork = nullptr, evA = nullptr, evB = nullptr;
+  double2 *A = nullptr, *B = nullptr, *Xi = nullptr, *Xt = nullptr;   // [M] padded systems
+  double2* buf[7] = {};                                               // (N+1) matrices each
+  double2 *Q = nullptr, *T = nullptr, *tmpF = nullptr, *tmpB = nullptr;   // 2*Cn, Cn, Cn, Cn matrices
+  int *tab2A = nullptr, *tab2T = nullptr, *tab0 = nullptr, *tab4F = nullptr, *tab4B = nullptr, *s_dev = nullptr;
+  float* norms = nullptr;
+  double *tau_fom = nullptr, *gk = nullptr;
+  std::vector<int> coo_ptr_h;     // [M][K+1] offsets into the member's COO arrays
+  int* coo_ptr = nullptr; int2* coo_idx = nullptr; double2* coo_val = nullptr;
+  std::vector<size_t> coo_member_off;
+  long long ws = 0;
+  bool attr_set = false;
+};
+
+#define BIG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+  return e_ == cudaErrorMemoryAllocation ? QOC_ENOMEM : QOC_ECUDA; } } while (0)
+
+template <class T> static int big_alloc(BigState* s, T** p, size_t n, std::string& err) {
+  if (n == 0) n = 1;
+  BIG_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  s->ws += (long long)(n * sizeof(T));
+  return QOC_OK;
+}
+static inline long long big_workspace(BigState* s) { return s ? s->ws : 0; }
+
+static inline void big_destroy(BigState* s) {
+  if (!s) return;
+  void* ptrs[] = {s->A, s->B, s->Xi, s->Xt, s->Q, s->T, s->tmpF, s->tmpB, s->tab2A, s->tab2T, s->tab0, s->tab4F, s->tab4B,
+                  s->s_dev, s->norms, s->tau_fom, s->gk, s->coo_ptr, s->coo_idx, s->coo_val};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& b : s->buf) if (b) cudaFree(b);
+  if (s->sA) cudaStreamDestroy(s->sA);
+  if (s->sB) cudaStreamDestroy(s->sB);
+  if (s->evFork) cudaEventDestroy(s->evFork);
+  if (s->evA) cudaEventDestroy(s->evA);
+  if (s->evB) cudaEventDestroy(s->evB);
+  delete s;
+}
+
+static inline int big_create(BigState** out, const qoc_desc& d, std::string& err, long long& ws_total) {
+  if (d.gradient == QOC_GRAD_EXACT) { err = "exact gradient is not implemented for D > 16"; return QOC_EUNSUPPORTED; }
+  BigState* s = new BigState();
+  *out = s;
+  s->d = d;
+  s->Dp = ((d.D + 63) / 64) * 64;
+  s->DD = (size_t)s->Dp * s->Dp;
+  s->unitary = d.sys_type == QOC_UNITARY_GATE;
+  // chunking: 16*(Dp/64)^2 ... tiles per GEMM; aim at two full waves of 2 CTAs/SM (592 CTAs) per lock-step launch
+  int tiles = (s->Dp / 64) * (s->Dp / 64);
+  int Cn = std::max(1, 592 / tiles);
+  Cn = std::min(Cn, std::max(1, d.N / 2));
+  s->Cn = Cn;
+  s->start.resize(Cn); s->len.resize(Cn);
+  for (int c = 0; c < Cn; c++) { int lo = (int)((long)c * d.N / Cn), hi = (int)((long)(c + 1) * d.N / Cn); s->start[c] = lo; s->len[c] = hi - lo; }
+  s->Lmax = *std::max_element(s->len.begin(), s->len.end());
+  int rc;
+  BIG_CUDA(cudaStreamCreateWithFlags(&s->sA, cudaStreamNonBlocking));
+  BIG_CUDA(cudaStreamCreateWithFlags(&s->sB, cudaStreamNonBlocking));
+  BIG_CUDA(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
+  BIG_CUDA(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
+  BIG_CUDA(cudaEventCreateWithFlags(&s->evB, cudaEventDisableTiming));
+  const size_t DD = s->DD;
+  if ((rc = big_alloc(s, &s->A, (size_t)d.M * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->B, (size_t)d.M * std::max(d.K, 1) * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Xi, (size_t)d.M * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Xt, (size_t)d.M * DD, err))) return rc;
+  for (auto& b : s->buf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Q, (size_t)2 * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->T, (size_t)Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->tmpF, (size_t)Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->tmpB, (size_t)Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->s_dev, 1, err))) return rc;
+  if ((rc = big_alloc(s, &s->norms, (size_t)d.N, err))) return rc;
+  if ((rc = big_alloc(s, &s->tau_fom, 4, err))) return rc;
+  if ((rc = big_alloc(s, &s->gk, (size_t)d.N * std::max(d.K, 1), err))) return rc;
+  // lock-step index tables
+  const int L = s->Lmax;
+  std::vector<int> t2A((size_t)L * Cn, -1), t2T((size_t)L * Cn, -1), t0(Cn), t4F((size_t)L * Cn, -1), t4B((size_t)L * Cn, -1);
+  for (int c = 0; c < Cn; c++) {
+    t0[c] = s->start[c];
+    for (int j = 0; j < L; j++) {
+      if (j >= 1 && j < s->len[c]) t2A[(size_t)j * Cn + c] = s->start[c] + j;
+      if (j == s->len[c] - 1) t2T[(size_t)j * Cn + c] = c;
+      if (j < s->len[c] - 1) { t4F[(size_t)j * Cn + c] = s->start[c] + j; t4B[(size_t)j * Cn + c] = s->start[c] + s->len[c] - 1 - j; }
+    }
+  }
+  auto up = [&](int** dst, const std::vector<int>& v) -> int {
+    int r = big_alloc(s, dst, v.size(), err); if (r) return r;
+    BIG_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return QOC_OK;
+  };
+  if ((rc = up(&s->tab2A, t2A)) || (rc = up(&s->tab2T, t2T)) || (rc = up(&s->tab0, t0)) || (rc = up(&s->tab4F, t4F)) || (rc = up(&s->tab4B, t4B))) return rc;
+  ws_total += s->ws;
+  return QOC_OK;
+}
+
+// upload [count] column-major D x D matrices into zero-padded Dp x Dp slots
+static int big_upload_padded(BigState* s, double2* dst, const double* src, size_t count, std::string& err) {
+  const int D = s->d.D, Dp = s->Dp;
+  BIG_CUDA(cudaMemset(dst, 0, count * s->DD * sizeof(double2)));
+  for (size_t m = 0; m < count; m++)
+    BIG_CUDA(cudaMemcpy2D(dst + m * s->DD, (size_t)Dp * sizeof(double2), src + m * 2 * (size_t)D * D, (size_t)D * sizeof(double2),
+                          (size_t)D * sizeof(double2), D, cudaMemcpyHostToDevice));
+  return QOC_OK;
+}
+
+static inline int big_set_system(BigState* s, const double* A, const double* B, const double* Xi, const double* Xt, int shared, std::string& err) {
+  const qoc_desc& d = s->d;
+  const int M = d.M, K = d.K, D = d.D;
+  const size_t dd = (size_t)D * D;
+  int rc;
+  auto rep = [&](double2* dst, const double* src, size_t per_member, bool sh) -> int {
+    for (int k = 0; k < M; k++)
+      if ((rc = big_upload_padded(s, dst + (size_t)k * per_member * s->DD, src + (sh ? 0 : (size_t)k * per_member * 2 * dd), per_member, err))) return rc;
+    return QOC_OK;
+  };
+  if ((rc = rep(s->A, A, 1, shared & QOC_SHARED_A))) return rc;
+  if (K > 0 && (rc = rep(s->B, B, K, shared & QOC_SHARED_B))) return rc;
+  if ((rc = rep(s->Xi, Xi, 1, shared & QOC_SHARED_XI))) return rc;
+  if ((rc = rep(s->Xt, Xt, 1, shared & QOC_SHARED_XT))) return rc;
+  // COO lists of the non-zeros of every control (indices in the padded matrix): tr(B W) = sum_nz B[a][b] W[b][a]
+  std::vector<int> ptr; std::vector<int2> idx; std::vector<double2> val;
+  s->coo_member_off.assign(M, 0);
+  for (int k = 0; k < M; k++) {
+    s->coo_member_off[k] = ptr.size();
+    const double* Bk = B + ((shared & QOC_SHARED_B) ? 0 : (size_t)k * K * 2 * dd);
+    for (int c = 0; c < K; c++) {
+      ptr.push_back((int)idx.size());
+      for (int col = 0; col < D; col++)
+        for (int row = 0; row < D; row++) {
+          double re = Bk[2 * ((size_t)c * dd + (size_t)col * D + row)], im = Bk[2 * ((size_t)c * dd + (size_t)col * D + row) + 1];
+          if (re != 0.0 || im != 0.0) { idx.push_back(make_int2(row, col)); val.push_back(make_double2(re, im)); }   // (a = row, b = col)
+        }
+    }
+    ptr.push_back((int)idx.size());
+  }
+  for (void* p : {(void*)s->coo_ptr, (void*)s->coo_idx, (void*)s->coo_val}) if (p) cudaFree(p);
+  s->coo_ptr = nullptr; s->coo_idx = nullptr; s->coo_val = nullptr;
+  if ((rc = big_alloc(s, &s->coo_ptr, ptr.size(), err)) || (rc = big_alloc(s, &s->coo_idx, idx.size(), err)) || (rc = big_alloc(s, &s->coo_val, val.size(), err))) return rc;
+  BIG_CUDA(cudaMemcpy(s->coo_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!idx.empty()) {
+    BIG_CUDA(cudaMemcpy(s->coo_idx, idx.data(), idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    BIG_CUDA(cudaMemcpy(s->coo_val, val.data(), val.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  return QOC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- launches
+static inline BatchedMat bmat(const double2* p, long stride, const int* table = nullptr, int offset = 0) { return BatchedMat{p, stride, table, offset}; }
+static inline EpiOut eout(BatchedMat m, double alpha = 1.0, int apow = 0, double ident = 0.0) { EpiOut e{}; e.m = m; e.alpha = alpha; e.alpha_pow2 = apow; e.ident = ident; e.naux = 0; return e; }
+static inline void eaux(EpiOut& e, BatchedMat m, double coef, int pow2 = 0) { e.aux[e.naux].m = m; e.aux[e.naux].coef = coef; e.aux[e.naux].pow2 = pow2; e.naux++; }
+
+static int big_gemm(BigState* s, int opA, int opB, GemmParams& p, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  typedef void (*kfn)(const GemmParams);
+  kfn fn = opA == 0 ? (opB == 0 ? zgemm_dmma_kernel<0, 0> : zgemm_dmma_kernel<0, 1>) : (opB == 0 ? zgemm_dmma_kernel<1, 0> : zgemm_dmma_kernel<1, 1>);
+  if (!s->attr_set) {
+    kfn all[] = {zgemm_dmma_kernel<0, 0>, zgemm_dmma_kernel<0, 1>, zgemm_dmma_kernel<1, 0>, zgemm_dmma_kernel<1, 1>};
+    for (kfn f : all) BIG_CUDA(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_BYTES));
+    s->attr_set = true;
+  }
+  p.D = s->Dp;
+  dim3 grid((s->Dp / 64) * (s->Dp / 64), p.batch);
+  fn<<<grid, GB_THREADS, GB_SMEM_BYTES, st>>>(p);
+  BIG_CUDA(cudaGetLastError());
+  stats.n_launches++; stats.launches_last_eval++;
+  return QOC_OK;
+}
+#define BIG_COUNT() do { BIG_CUDA(cudaGetLastError()); stats.n_launches++; stats.launches_last_eval++; } while (0)
+
+// phase 1: propagators of member k for pulse x (device pointer to [N][K]) into buf[5] (P); returns via s_host
+static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const qoc_desc& d = s->d;
+  const size_t DD = s->DD; const long sd = (long)DD;
+  const int N = d.N;
+  double2 *G = s->buf[0], *G2 = s->buf[1], *Y1 = s->buf[2], *L8 = s->buf[3], *R8 = s->buf[4], *P = s->buf[5], *P2 = s->buf[6];
+  dim3 ga((unsigned)((DD + 255) / 256), (N + 63) / 64);
+  big_assemble_kernel<<<ga, 256, 0, st>>>(s->A + (size_t)k * DD, s->B + (size_t)k * std::max(d.K, 1) * DD, x_dev, G, (int)DD, d.K, N, 64, d.T / N, 0);
+  BIG_COUNT();
+  big_norm_kernel<<<N, 256, 0, st>>>(G, s->Dp, s->norms);
+  BIG_COUNT();
+  big_scale_power_kernel<<<1, 256, 0, st>>>(s->norms, N, (float)(d.expm_theta > 0 ? d.expm_theta : 0.0694), s->s_dev);
+  BIG_COUNT();
+  int rc;
+  GemmParams p{};
+  p.batch = N; p.s_ptr = s->s_dev;
+  // G2 = (G/2^s)^2 ; Y1 = x1 G/2^s + x2 G2
+  p.A = bmat(G, sd); p.B = bmat(G, sd); p.nout = 2;
+  p.out[0] = eout(bmat(G2, sd), 1.0, 2);
+  p.out[1] = eout(bmat(Y1, sd), BT8_X2, 2); eaux(p.out[1], bmat(G, sd), BT8_X1, 1);
+  if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+  // G4 = G2 * Y1 ; L8 = x3 G2 + G4 ; R8 = x4 I + x5 G/2^s + x6 G2 + x7 G4
+  p.A = bmat(G2, sd); p.B = bmat(Y1, sd);
+  p.out[0] = eout(bmat(L8, sd), 1.0, 0); eaux(p.out[0], bmat(G2, sd), BT8_X3);
+  p.out[1] = eout(bmat(R8, sd), BT8_X7, 0, BT8_X4); eaux(p.out[1], bmat(G, sd), BT8_X5, 1); eaux(p.out[1], bmat(G2, sd), BT8_X6);
+  if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+  // P = I + G/2^s + y2 G2 + L8 * R8
+  p.A = bmat(L8, sd); p.B = bmat(R8, sd); p.nout = 1;
+  p.out[0] = eout(bmat(P, sd), 1.0, 0, 1.0); eaux(p.out[0], bmat(G, sd), 1.0, 1); eaux(p.out[0], bmat(G2, sd), BT8_Y2);
+  if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+  // squarings: the count lives on the device; one small synchronising read per evaluation
+  int s_host = 0;
+  BIG_CUDA(cudaMemcpyAsync(&s_host, s->s_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  BIG_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < s_host; j++) {
+    GemmParams q{};
+    q.batch = N; q.A = bmat(P, sd); q.B = bmat(P, sd); q.nout = 1; q.out[0] = eout(bmat(P2, sd));
+    if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+    std::swap(P, P2);
+  }
+  if (P != s->buf[5]) std::swap(s->buf[5], s->buf[6]);   // keep "buf[5] is P"
+  return QOC_OK;
+}
+
+// phase 2: chunk totals T_c (batch Cn, Lmax-1 lock steps)
+static int big_chunk_totals(BigState* s, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const long sd = (long)s->DD; const int Cn = s->Cn;
+  double2* P = s->buf[5];
+  int rc;
+  for (int c = 0; c < Cn; c++)
+    if (s->len[c] == 1) BIG_CUDA(cudaMemcpyAsync(s->T + (size_t)c * s->DD, P + (size_t)s->start[c] * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  for (int j = 1; j < s->Lmax; j++) {
+    GemmParams p{};
+    p.batch = Cn;
+    p.A = bmat(P, sd, s->tab2A + (size_t)j * Cn);
+    p.B = j == 1 ? bmat(P, sd, s->tab0) : bmat(s->Q + (size_t)((j - 1) & 1) * Cn * s->DD, sd);
+    p.nout = 2;
+    p.out[0] = eout(bmat(s->Q + (size_t)(j & 1) * Cn * s->DD, sd));
+    p.out[1] = eout(bmat(s->T, sd, s->tab2T + (size_t)j * Cn));
+    if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+  }
+  return QOC_OK;
+}
+
+static int big_eval_member(BigState* s, int k, const double* x_dev, int want_grad, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const qoc_desc& d = s->d;
+  const size_t DD = s->DD; const long sd = (long)DD;
+  const int N = d.N, Cn = s->Cn, U = s->unitary;
+  int rc;
+  if ((rc = big_propagators_phase(s, k, x_dev, st, err, stats))) return rc;
+  double2 *P = s->buf[5], *S = s->buf[1], *C = s->buf[2], *W = s->buf[3];
+  if ((rc = big_chunk_totals(s, st, err, stats))) return rc;
+  // ---- phase 3: boundary states (stream sA) and boundary costates (stream sB), short sequential chains ----
+  BIG_CUDA(cudaMemcpyAsync(S, s->Xi + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(C + (size_t)N * DD, s->Xt + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaEventRecord(s->evFork, st));
+  BIG_CUDA(cudaStreamWaitEvent(s->sA, s->evFork, 0));
+  BIG_CUDA(cudaStreamWaitEvent(s->sB, s->evFork, 0));
+  for (int c = 0; c < Cn; c++) {          // S[start_{c+1}] = T_c S[start_c] (T_c')
+    const double2* Tc = s->T + (size_t)c * DD;
+    double2* Sin = S + (size_t)s->start[c] * DD;
+    double2* Sout = S + (size_t)(s->start[c] + s->len[c]) * DD;
+    GemmParams p{}; p.batch = 1; p.nout = 1;
+    if (U) { p.A = bmat(Tc, 0); p.B = bmat(Sin, 0); p.out[0] = eout(bmat(Sout, 0)); if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc; }
+    else {
+      p.A = bmat(Sin, 0); p.B = bmat(Tc, 0); p.out[0] = eout(bmat(s->tmpF, 0)); if ((rc = big_gemm(s, 0, 1, p, s->sA, err, stats))) return rc;
+      p.A = bmat(Tc, 0); p.B = bmat(s->tmpF, 0); p.out[0] = eout(bmat(Sout, 0)); if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc;
+    }
+  }
+  if (want_grad) {
+    for (int c = Cn - 1; c >= 0; c--) {   // C[start_c] = T_c' C[end_c] (T_c)
+      const double2* Tc = s->T + (size_t)c * DD;
+      double2* Cin = C + (size_t)(s->start[c] + s->len[c]) * DD;
+      double2* Cout = C + (size_t)s->start[c] * DD;
+      GemmParams p{}; p.batch = 1; p.nout = 1;
+      if (U) { p.A = bmat(Tc, 0); p.B = bmat(Cin, 0); p.out[0] = eout(bmat(Cout, 0)); if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc; }
+      else {
+        p.A = bmat(Cin, 0); p.B = bmat(Tc, 0); p.out[0] = eout(bmat(s->tmpB, 0)); if ((rc = big_gemm(s, 0, 0, p, s->sB, err, stats))) return rc;
+        p.A = bmat(Tc, 0); p.B = bmat(s->tmpB, 0); p.out[0] = eout(bmat(Cout, 0)); if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc;
+      }
+    }
+    // ---- phase 4: lock-step sweeps inside the chunks, forward on sA, backward on sB ----
+    for (int j = 0; j < s->Lmax - 1; j++) {
+      const int* tF = s->tab4F + (size_t)j * Cn;
+      const int* tB = s->tab4B + (size_t)j * Cn;
+      GemmParams p{}; p.batch = Cn; p.nout = 1;
+      if (U) {
+        p.A = bmat(P, sd, tF); p.B = bmat(S, sd, tF); p.out[0] = eout(bmat(S, sd, tF, 1));                   // S[t+1] = P_t S_t
+        if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc;
+        p.A = bmat(P, sd, tB); p.B = bmat(C, sd, tB, 1); p.out[0] = eout(bmat(C, sd, tB));                   // C[t] = P_t' C[t+1]
+        if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc;
+      } else {
+        p.A = bmat(S, sd, tF); p.B = bmat(P, sd, tF); p.out[0] = eout(bmat(s->tmpF, sd));                    // S_t P_t'
+        if ((rc = big_gemm(s, 0, 1, p, s->sA, err, stats))) return rc;
+        p.A = bmat(P, sd, tF); p.B = bmat(s->tmpF, sd); p.out[0] = eout(bmat(S, sd, tF, 1));                 // P_t (S_t P_t')
+        if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc;
+        p.A = bmat(C, sd, tB, 1); p.B = bmat(P, sd, tB); p.out[0] = eout(bmat(s->tmpB, sd));                 // C[t+1] P_t
+        if ((rc = big_gemm(s, 0, 0, p, s->sB, err, stats))) return rc;
+        p.A = bmat(P, sd, tB); p.B = bmat(s->tmpB, sd); p.out[0] = eout(bmat(C, sd, tB));                    // P_t' (C[t+1] P_t)
+        if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc;
+      }
+    }
+  }
+  BIG_CUDA(cudaEventRecord(s->evA, s->sA));
+  BIG_CUDA(cudaEventRecord(s->evB, s->sB));
+  BIG_CUDA(cudaStreamWaitEvent(st, s->evA, 0));
+  BIG_CUDA(cudaStreamWaitEvent(st, s->evB, 0));
+  // ---- figure of merit from S[N] and Xt ----
+  const double invD2 = 1.0 / ((double)d.D * d.D);
+  if (U) big_fom_kernel<<<1, 256, 0, st>>>(S + (size_t)N * DD, s->Xt + (size_t)k * DD, (int)DD, 1, invD2, s->tau_fom);
+  else big_fom_kernel<<<1, 256, 0, st>>>(s->Xt + (size_t)k * DD, S + (size_t)N * DD, (int)DD, 0, invD2, s->tau_fom);
+  BIG_COUNT();
+  if (!want_grad) return QOC_OK;
+  // ---- phase 5: W_t for all slices, then trace-dots ----
+  {
+    GemmParams p{}; p.batch = N; p.nout = 1;
+    p.A = bmat(S, sd); p.B = bmat(C, sd); p.out[0] = eout(bmat(W, sd));                                      // S_t C_t'
+    if ((rc = big_gemm(s, 0, 1, p, st, err, stats))) return rc;
+    if (!U) {
+      p.A = bmat(C, sd); p.B = bmat(S, sd); p.out[0] = eout(bmat(W, sd), -1.0); eaux(p.out[0], bmat(W, sd), 1.0);   // W - C_t' S_t
+      if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
+    }
+  }
+  if (d.K > 0) {
+    BigTraceParams tp;
+    tp.W = W; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
+    tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.g = s->gk;
+    big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
+    BIG_COUNT();
+  }
+  return QOC_OK;
+}
+
+static inline int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
+                           std::string& err, qoc_stats& stats) {
+  const qoc_desc& d = s->d;
+  const int NK = d.N * d.K;
+  int rc;
+  for (int r = 0; r < d.R; r++)
+    for (int k = 0; k < d.M; k++) {
+      if ((rc = big_eval_member(s, k, x_dev + (size_t)r * NK, want_grad, st, err, stats))) return rc;
+      big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev + (size_t)r * (NK + 1), s->tau_fom, s->gk, wts_dev, k, NK, k == 0, want_grad);
+      BIG_COUNT();
+    }
+  return QOC_OK;
+}
+
+// copy [count] padded matrices into a dense D x D output
+static int big_unpad(BigState* s, double2* dst, const double2* src, size_t count, cudaStream_t st, std::string& err) {
+  const int D = s->d.D, Dp = s->Dp;
+  if (D == Dp) { BIG_CUDA(cudaMemcpyAsync(dst, src, count * s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st)); return QOC_OK; }
+  for (size_t m = 0; m < count; m++)
+    BIG_CUDA(cudaMemcpy2DAsync(dst + m * (size_t)D * D, (size_t)D * sizeof(double2), src + m * s->DD, (size_t)Dp * sizeof(double2),
+                               (size_t)D * sizeof(double2), D, cudaMemcpyDeviceToDevice, st));
+  return QOC_OK;
+}
+
+static inline int big_propagators(BigState* s, const double* x_dev, double2* out, int mode, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const qoc_desc& d = s->d;
+  const int NK = d.N * d.K;
+  int rc;
+  for (int r = 0; r < d.R; r++)
+    for (int k = 0; k < d.M; k++) {
+      const double2* src;
+      if (mode == 0) { if ((rc = big_propagators_phase(s, k, x_dev + (size_t)r * NK, st, err, stats))) return rc; src = s->buf[5]; }
+      else {
+        dim3 ga((unsigned)((s->DD + 255) / 256), (d.N + 63) / 64);
+        big_assemble_kernel<<<ga, 256, 0, st>>>(s->A + (size_t)k * s->DD, s->B + (size_t)k * std::max(d.K, 1) * s->DD, x_dev + (size_t)r * NK,
+                                                s->buf[0], (int)s->DD, d.K, d.N, 64, d.T / d.N, mode);
+        BIG_COUNT();
+        src = s->buf[0];
+      }
+      if ((rc = big_unpad(s, out + ((size_t)r * d.M + k) * d.N * d.D * d.D, src, d.N, st, err))) return rc;
+    }
+  return QOC_OK;
+}
+
+static inline int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const qoc_desc& d = s->d;
+  const int NK = d.N * d.K;
+  const size_t DD = s->DD;
+  int rc;
+  for (int r = 0; r < d.R; r++)
+    for (int k = 0; k < d.M; k++) {
+      if ((rc = big_propagators_phase(s, k, x_dev + (size_t)r * NK, st, err, stats))) return rc;
+      if ((rc = big_chunk_totals(s, st, err, stats))) return rc;
+      const double2* cur = s->T;                       // U = T_{Cn-1} ... T_0
+      for (int c = 1; c < s->Cn; c++) {
+        double2* dst = s->Q + (size_t)(c & 1) * s->Cn * DD;
+        GemmParams p{}; p.batch = 1; p.nout = 1;
+        p.A = bmat(s->T + (size_t)c * DD, 0); p.B = bmat(cur, 0); p.out[0] = eout(bmat(dst, 0));
+        if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+        cur = dst;
+      }
+      if ((rc = big_unpad(s, out + ((size_t)r * d.M + k) * d.D * d.D, cur, 1, st, err))) return rc;
+    }
+  return QOC_OK;
+}
+
 }  // namespace qoc

@@ -1,0 +1,78 @@
+"""GPU parity of the large-dimension path (D > 16: tiled DMMA GEMM pipeline) against the numpy oracle."""
+import numpy as np
+import pytest
+
+import quoptimalcontrol_jl_b200 as qoc
+from oracle import grape_oracle as orc
+from conftest import assert_parity, random_system
+
+pytestmark = pytest.mark.gpu
+SYS = {"state": orc.STATE_TRANSFER, "unitary": orc.UNITARY_GATE, "coherence": orc.COHERENCE_TRANSFER}
+
+
+@pytest.mark.parametrize("D,N", [(64, 12), (20, 7), (100, 5), (128, 9), (64, 1), (64, 2), (64, 3)])
+@pytest.mark.parametrize("sys_name", ["state", "unitary", "coherence"])
+def test_first_order_dense_random(D, N, sys_name):
+    K, T = 3, 0.8
+    A, B, Xi, Xt = random_system(D, K, seed=600 + D + N, hermitian=(sys_name != "coherence"),
+                                 unitary_targets=(sys_name == "unitary"))
+    x = np.random.default_rng(D + N).uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, SYS[sys_name]) as ev:
+        F, G = ev.eval(x)
+        F0, _ = ev.eval(x, want_grad=False)
+        assert ev.stats()["path"] == 2
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, SYS[sys_name])
+    assert_parity(F, G, Fo, Go)
+    assert_parity(F0, None, Fo, None)
+
+
+def test_static_sign_and_ensemble():
+    D, K, N, T, M = 64, 2, 6, 0.5, 3
+    members = [random_system(D, K, seed=700 + k, unitary_targets=True) for k in range(M)]
+    wts = [0.5, 0.2, 0.3]
+    x = np.random.default_rng(5).uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator(members, T, N, orc.UNITARY_GATE, wts=wts, convention="static") as ev:
+        F, G = ev.eval(x)
+    Fo, Go = orc.ensemble_fom_and_gradient(members, wts, x, T, orc.UNITARY_GATE, orc.REF_STATIC)
+    assert_parity(F, G, Fo, Go)
+
+
+def test_large_norm_squarings():
+    D, K, N, T = 64, 2, 4, 2.0
+    A, B, Xi, Xt = random_system(D, K, seed=9, scale=6.0)
+    x = np.random.default_rng(1).uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER) as ev:
+        F, G = ev.eval(x)
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert_parity(F, G, Fo, Go, ftol=1e-9, gtol=1e-7)
+
+
+@pytest.mark.parametrize("n,N", [(6, 40), (8, 6)])
+def test_config5_reduced(n, N):
+    cfg = qoc.configs.config5(N=N, n=n)
+    A, B, Xi, Xt = cfg["members"][0]
+    with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"]) as ev:
+        F, G = ev.eval(cfg["x"])
+    Fo, Go = orc.fom_and_gradient_grape(A, B, cfg["x"], cfg["T"], Xi, Xt, cfg["sys_type"])
+    assert_parity(F, G, Fo, Go)
+
+
+def test_propagators_and_total_big():
+    D, K, N, T = 64, 2, 9, 1.1
+    A, B, _, _ = random_system(D, K, seed=31)
+    x = np.random.default_rng(2).uniform(-1, 1, (K, N))
+    dt = T / N
+    P = qoc.pw_prop_save(A, B, x, K, N, dt)
+    for a, b in zip(P, orc.pw_prop_save(A, B, x, dt)):
+        assert np.max(np.abs(a - b)) < 1e-13
+    for a, b in zip(qoc.pw_ham_save(A, B, x, K, N), orc.pw_ham_save(A, B, x)):
+        assert np.max(np.abs(a - b)) < 1e-14
+    I = np.eye(D, dtype=complex)
+    assert np.max(np.abs(qoc.pw_evolve(A, B, x, K, dt, N, I) - orc.pw_evolve(A, B, x, dt, I))) < 1e-12
+
+
+def test_exact_unsupported_is_loud():
+    A, B, Xi, Xt = random_system(64, 1, seed=1)
+    with pytest.raises(qoc.QocError) as e:
+        qoc.GrapeEvaluator([(A, B, Xi, Xt)], 1.0, 4, orc.STATE_TRANSFER, gradient="exact")
+    assert e.value.status == qoc._lib.QOC_EUNSUPPORTED
