@@ -24,7 +24,7 @@ struct qoc_handle {
   int kring_count = 0;
   // derived small-path geometry
   int path = 0, NB = 1, CPW = 1, pack_mode = 0, n_groups = 0, n_inner = 0, n_sysgroups = 0, nmat = 0;
-  int have_P = 0, sys_in_smem = 0, smem_bytes = 0;
+  int have_P = 0, sys_in_smem = 0, smem_bytes = 0, tb_bytes = 0, herm = 0;
   int NK = 0, red_chunk = 0, red_nchunks = 0;
   bool system_set = false;
   // device buffers
@@ -133,9 +133,10 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     h->nmat = 1 + d.K + (d.gradient == QOC_GRAD_EXACT ? d.K : 0);
     h->have_P = h->n_groups < 148 * 8;   // too few chains to fill the GPU: exponentials go slice-parallel
     const size_t E = (size_t)h->NB * h->NB * 64;
+    h->tb_bytes = 4 * h->NB * h->NB * 2 * TB_PLANE * (int)sizeof(double);     // per-warp transpose tiles
     size_t smem = (size_t)4 * h->nmat * E * sizeof(double2);
-    h->sys_in_smem = smem <= 96 * 1024;
-    h->smem_bytes = h->sys_in_smem ? (int)smem : 0;
+    h->sys_in_smem = smem + h->tb_bytes <= 96 * 1024;
+    h->smem_bytes = h->tb_bytes + (h->sys_in_smem ? (int)smem : 0);
     CR(dev_alloc(h, &h->sys, (size_t)h->n_sysgroups * h->nmat * E));
     CR(dev_alloc(h, &h->xi, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->xt, (size_t)h->n_sysgroups * E));
@@ -186,8 +187,9 @@ extern "C" int qoc_destroy(qoc_handle* h) {
 
 // ------------------------------------------------------------------------------------------------ set_system
 static int pack_one(qoc_handle* h, const double2* src_dev, int n_src, long src_stride, int transpose,
-                    double2* dst, int nmat_dst, int mat_dst, int pack_mode) {
+                    double2* dst, int nmat_dst, int mat_dst, int pack_mode, double sre = 1.0, double sim = 0.0) {
   PackParams pp;
+  pp.scale_re = sre; pp.scale_im = sim;
   pp.D = h->d.D; pp.NB = h->NB; pp.CPW = h->CPW; pp.n_og = h->n_sysgroups; pp.nmat_dst = nmat_dst; pp.mat_dst = mat_dst;
   pp.transpose = transpose; pp.pack_mode = pack_mode; pp.n_src = n_src; pp.src_stride = src_stride; pp.src = src_dev; pp.dst = dst;
   long total = (long)h->n_sysgroups * h->NB * h->NB * 64;
@@ -213,6 +215,23 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
   }
   // small path: stage raw matrices on the device, then pack into the warp layout
   const int member_mode = h->pack_mode;   // 0: slot -> member og*CPW+s ; 1: all slots -> member og
+  const double dt = d.T / d.N;              // A, B are packed pre-multiplied by -i*dt
+  const int tr_states = d.sys_type == QOC_UNITARY_GATE ? 1 : 0;   // the unitary chain runs on S^T, C^T
+  {  // Hermitian drift and controls  =>  anti-Hermitian generators (exact elementwise test)
+    auto is_herm = [&](const double* Mx) {
+      for (int c = 0; c < d.D; c++)
+        for (int r = 0; r <= c; r++) {
+          const double* a = Mx + 2 * ((size_t)c * d.D + r); const double* b = Mx + 2 * ((size_t)r * d.D + c);
+          if (a[0] != b[0] || a[1] != -b[1]) return false;
+        }
+      return true;
+    };
+    bool herm = true;
+    const int nA = (shared_flags & QOC_SHARED_A) ? 1 : d.M, nB = (shared_flags & QOC_SHARED_B) ? 1 : d.M;
+    for (int k = 0; k < nA && herm; k++) herm = is_herm(A + 2 * (size_t)k * DD);
+    for (int k = 0; k < nB * d.K && herm; k++) herm = is_herm(B + 2 * (size_t)k * DD);
+    h->herm = herm ? 1 : 0;
+  }
   auto upload = [&](const double* src, size_t count) -> int {
     QOC_CUDA(h, cudaMemcpyAsync(h->staging, src, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     return QOC_OK;
@@ -221,27 +240,27 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
   {  // A
     bool sh = shared_flags & QOC_SHARED_A;
     if ((rc = upload(A, (sh ? 1 : (size_t)d.M) * DD)) != QOC_OK) return rc;
-    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->sys, h->nmat, 0, member_mode)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->sys, h->nmat, 0, member_mode, 0.0, -dt)) != QOC_OK) return rc;
     QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   if (d.K > 0) {  // B (and transposed copies for the exact gradient)
     bool sh = shared_flags & QOC_SHARED_B;
     if ((rc = upload(B, (sh ? 1 : (size_t)d.M) * d.K * DD)) != QOC_OK) return rc;
     for (int c = 0; c < d.K; c++) {
-      if ((rc = pack_one(h, h->staging + (size_t)c * DD, sh ? 1 : d.M, sh ? 0 : (long)(d.K * DD), 0, h->sys, h->nmat, 1 + c, member_mode)) != QOC_OK) return rc;
+      if ((rc = pack_one(h, h->staging + (size_t)c * DD, sh ? 1 : d.M, sh ? 0 : (long)(d.K * DD), 0, h->sys, h->nmat, 1 + c, member_mode, 0.0, -dt)) != QOC_OK) return rc;
       if (d.gradient == QOC_GRAD_EXACT)
-        if ((rc = pack_one(h, h->staging + (size_t)c * DD, sh ? 1 : d.M, sh ? 0 : (long)(d.K * DD), 1, h->sys, h->nmat, 1 + d.K + c, member_mode)) != QOC_OK) return rc;
+        if ((rc = pack_one(h, h->staging + (size_t)c * DD, sh ? 1 : d.M, sh ? 0 : (long)(d.K * DD), 1, h->sys, h->nmat, 1 + d.K + c, member_mode, 0.0, -dt)) != QOC_OK) return rc;
     }
     QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   {  // Xi, Xt
     bool sh = shared_flags & QOC_SHARED_XI;
     if ((rc = upload(Xi, (sh ? 1 : (size_t)d.M) * DD)) != QOC_OK) return rc;
-    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->xi, 1, 0, member_mode)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, tr_states, h->xi, 1, 0, member_mode)) != QOC_OK) return rc;
     QOC_CUDA(h, cudaStreamSynchronize(h->stream));
     sh = shared_flags & QOC_SHARED_XT;
     if ((rc = upload(Xt, (sh ? 1 : (size_t)d.M) * DD)) != QOC_OK) return rc;
-    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, 0, h->xt, 1, 0, member_mode)) != QOC_OK) return rc;
+    if ((rc = pack_one(h, h->staging, sh ? 1 : d.M, sh ? 0 : (long)DD, tr_states, h->xt, 1, 0, member_mode)) != QOC_OK) return rc;
     QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   }
   {  // identity (initial state of qoc_total_propagator)
@@ -264,6 +283,7 @@ static SmallParams small_params(qoc_handle* h, const double* x_dev) {
   p.sys_in_smem = h->sys_in_smem; p.have_P = h->have_P;
   p.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1;
   p.fom_exact = d.gradient == QOC_GRAD_EXACT;
+  p.herm = h->herm;
   p.dt = d.T / d.N; p.theta = d.expm_theta;
   p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev;
   p.storeP = h->storeP; p.storeS = h->storeS; p.fomc = h->fomc; p.gradc = h->gradc; p.out_final = nullptr;
@@ -273,7 +293,7 @@ static SliceParams slice_params(qoc_handle* h, const double* x_dev) {
   const qoc_desc& d = h->d;
   SliceParams s;
   s.D = d.D; s.N = d.N; s.K = d.K; s.M = d.M; s.R = d.R; s.pack_mode = h->pack_mode; s.n_groups = h->n_groups;
-  s.n_inner = h->n_inner; s.nmat = h->nmat; s.dt = d.T / d.N; s.theta = d.expm_theta;
+  s.n_inner = h->n_inner; s.nmat = h->nmat; s.herm = h->herm; s.dt = d.T / d.N; s.theta = d.expm_theta;
   s.sys = h->sys; s.x = x_dev; s.storeP = nullptr; s.out_user = nullptr; s.mode = 0;
   return s;
 }
@@ -286,7 +306,7 @@ static int launch_chain(qoc_handle* h, const SmallParams& p, int sys, int grad, 
 }
 static int launch_slices(qoc_handle* h, const SliceParams& s, cudaStream_t st) {
   long warps = (long)h->n_groups * h->d.N;
-  pick_slices(h->NB, h->CPW)<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(s);
+  pick_slices(h->NB, h->CPW)<<<(unsigned)((warps + 3) / 4), 128, h->tb_bytes, st>>>(s);
   return launch_check(h, "expm_slices_kernel");
 }
 
@@ -296,20 +316,20 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   SmallParams p = small_params(h, x_dev);
   const int sys = d.sys_type == QOC_UNITARY_GATE ? SYS_UNITARY : SYS_DENSITY;
   const int grad = !want_grad ? GRAD_NONE : (d.gradient == QOC_GRAD_EXACT ? GRAD_EXACT : GRAD_FIRST);
+  const int slot = h->kring_count % qoc_handle::KRING;
+  QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if (h->have_P) {
     SliceParams s = slice_params(h, x_dev);
     s.storeP = h->storeP;
     if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
   }
-  const int slot = h->kring_count % qoc_handle::KRING;
-  QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st));
   h->kring_count++;
-  dim3 g1((h->NK + 1 + 255) / 256, h->red_nchunks, d.R);
+  dim3 g1((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R), h->red_nchunks);
   reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->part, d.M, h->NK, h->red_chunk, h->red_nchunks);
   if ((rc = launch_check(h, "reduce_members_pass1")) != QOC_OK) return rc;
-  dim3 g2((h->NK + 1 + 255) / 256, d.R);
+  dim3 g2((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R));
   reduce_members_pass2<<<g2, 256, 0, st>>>(h->part, fg_dev, h->NK, h->red_nchunks);
   return launch_check(h, "reduce_members_pass2");
 }

@@ -37,9 +37,10 @@ struct SmallParams {
   int have_P;          // propagators were precomputed into storeP by expm_slices_kernel
   int sign_static;     // first-order UnitaryGate: +1 grad_func! (in-place), -1 grad_func (static)
   int fom_exact;       // figure of merit of the exact (ADGRAPE / C1) functional even when no gradient is asked
+  int herm;            // drift and all controls are Hermitian (host-checked): generator is anti-Hermitian
   double dt, theta;
-  const double2* sys;  // [n_sysgroups][nmat][NB*NB*2*32]
-  const double2* xi;   // [n_sysgroups][NB*NB*2*32]
+  const double2* sys;  // [n_sysgroups][nmat][NB*NB*2*32], pre-multiplied by -i*dt
+  const double2* xi;   // [n_sysgroups][NB*NB*2*32]; UnitaryGate: packed transposed (the chain runs on S^T)
   const double2* xt;
   const double* x;     // [R][N][K]  (= the reference's K x N column-major control_array per pulse)
   double2* storeP;     // [n_groups][N][NB*NB*2*32]
@@ -53,6 +54,14 @@ template <int NB> __host__ __device__ constexpr int cm_elems() { return NB * NB 
 
 // 1-norm upper bound (column sums of |re|+|im|), warp-uniform max over all packed chains; float is enough
 // for a scaling decision and is rounded up.
+// float upper bound of |x| from the high word of the double, on the integer pipe (the FP64 pipe is the
+// bottleneck resource): exponent re-biased by 1023-127 = 896, 20 mantissa bits kept, rounded up.
+__device__ __forceinline__ float abs_upper_f32(double x) {
+  int hi = __double2hiint(x) & 0x7fffffff;
+  int e = hi - 0x38000000;                       // (896 << 20)
+  e = e < 0 ? 0 : (e > 0x0fdfffff ? 0x0fdfffff : e);
+  return __int_as_float((e << 3) + 8);
+}
 template <int NB> __device__ __forceinline__ float cm_norm1_bound(const CM<NB>& x) {
   float best = 0.f;
 #pragma unroll
@@ -61,7 +70,7 @@ template <int NB> __device__ __forceinline__ float cm_norm1_bound(const CM<NB>& 
     for (int e = 0; e < 2; e++) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < NB; i++) s += (float)(fabs(x.re[i][j][e]) + fabs(x.im[i][j][e]));
+      for (int i = 0; i < NB; i++) s += abs_upper_f32(x.re[i][j][e]) + abs_upper_f32(x.im[i][j][e]);
       s += __shfl_xor_sync(FULL_MASK, s, 4);
       s += __shfl_xor_sync(FULL_MASK, s, 8);
       s += __shfl_xor_sync(FULL_MASK, s, 16);
@@ -77,93 +86,95 @@ __device__ __forceinline__ int scaling_power(float nrm, float theta) {
   return s > 60 ? 60 : s;
 }
 
-// P = exp(G): scaling, T8 in 3 products, s squarings.
-template <int NB> __device__ __forceinline__ CM<NB> expm_t8(const Lane& L, CM<NB> G, float theta) {
-  int s = scaling_power(cm_norm1_bound<NB>(G), theta);
+// P = exp(G): scaling, T8 in 3 NT products, s squarings.  `herm`: G is anti-Hermitian (Hermitian drift and
+// controls, checked on the host), so G^T = -conj(G) and (G^2)^T = conj(G^2) cost no data movement.
+template <int NB> __device__ __forceinline__ CM<NB> expm_t8(const Lane& L, CM<NB> G, float theta, bool herm, double* tb) {
+  const int s = scaling_power(cm_norm1_bound<NB>(G), theta);
   if (s) G = cm_scale<NB>(G, scalbn(1.0, -s));
-  FA<NB> Ga = to_A<NB>(L, G);
-  FB<NB> Gb = to_B<NB>(L, G);
-  CM<NB> G2 = mul<NB>(Ga, Gb);
-  CM<NB> Y1 = cm_scale<NB>(G, T8_X1); cm_axpy<NB>(Y1, T8_X2, G2);
-  CM<NB> G4 = mul<NB>(to_A<NB>(L, G2), to_B<NB>(L, Y1));
+  const CM<NB> Gt = herm ? cm_negconj<NB>(G) : transpose<NB>(L, G, tb);
+  const CM<NB> G2 = mul_nt<NB>(G, Gt);
+  const CM<NB> G2t = herm ? cm_conj<NB>(G2) : transpose<NB>(L, G2, tb);
+  CM<NB> Y1t = cm_scale<NB>(Gt, T8_X1); cm_axpy<NB>(Y1t, T8_X2, G2t);
+  const CM<NB> G4 = mul_nt<NB>(G2, Y1t);
+  const CM<NB> G4t = transpose<NB>(L, G4, tb);
   CM<NB> L8 = G4; cm_axpy<NB>(L8, T8_X3, G2);
-  CM<NB> R8 = cm_scale<NB>(G, T8_X5); cm_axpy<NB>(R8, T8_X6, G2); cm_axpy<NB>(R8, T8_X7, G4);
-  cm_add_identity<NB>(L, R8, T8_X4);
-  CM<NB> P = mul<NB>(to_A<NB>(L, L8), to_B<NB>(L, R8));
-  cm_axpy<NB>(P, 1.0, G); cm_axpy<NB>(P, T8_Y2, G2); cm_add_identity<NB>(L, P, 1.0);
-  for (int j = 0; j < s; j++) P = mul<NB>(to_A<NB>(L, P), to_B<NB>(L, P));
+  CM<NB> R8t = cm_scale<NB>(Gt, T8_X5); cm_axpy<NB>(R8t, T8_X6, G2t); cm_axpy<NB>(R8t, T8_X7, G4t);
+  cm_add_identity<NB>(L, R8t, T8_X4);
+  CM<NB> P = G; cm_axpy<NB>(P, T8_Y2, G2); cm_add_identity<NB>(L, P, 1.0);
+  mul_nt_acc<NB>(L8, R8t, P);
+  for (int j = 0; j < s; j++) { const CM<NB> Pt = transpose<NB>(L, P, tb); P = mul_nt<NB>(P, Pt); }
   return P;
 }
 
 // Frechet derivative L_exp(G, Y) of the same scheme (derivative of each of the three products and of every
 // squaring).  Identity tr(W * L(G,E)) = tr(L(G,W) * E) lets ONE call per slice serve all K controls.
-template <int NB> __device__ __forceinline__ CM<NB> frechet_t8(const Lane& L, CM<NB> G, CM<NB> Y, float theta) {
-  int s = scaling_power(cm_norm1_bound<NB>(G), theta);
+template <int NB> __device__ __forceinline__ CM<NB> frechet_t8(const Lane& L, CM<NB> G, CM<NB> Y, float theta, bool herm, double* tb) {
+  const int s = scaling_power(cm_norm1_bound<NB>(G), theta);
   if (s) { double sc = scalbn(1.0, -s); G = cm_scale<NB>(G, sc); Y = cm_scale<NB>(Y, sc); }
-  FA<NB> Ga = to_A<NB>(L, G);
-  FB<NB> Gb = to_B<NB>(L, G);
-  CM<NB> G2 = mul<NB>(Ga, Gb);
-  CM<NB> dG2 = mul<NB>(to_A<NB>(L, Y), Gb);
-  mul_acc<NB>(Ga, to_B<NB>(L, Y), dG2);
-  CM<NB> Y1 = cm_scale<NB>(G, T8_X1); cm_axpy<NB>(Y1, T8_X2, G2);
-  FB<NB> Y1b = to_B<NB>(L, Y1);
-  FA<NB> G2a = to_A<NB>(L, G2);
-  CM<NB> G4 = mul<NB>(G2a, Y1b);
-  CM<NB> dY1 = cm_scale<NB>(Y, T8_X1); cm_axpy<NB>(dY1, T8_X2, dG2);
-  CM<NB> dG4 = mul<NB>(to_A<NB>(L, dG2), Y1b);
-  mul_acc<NB>(G2a, to_B<NB>(L, dY1), dG4);
+  const CM<NB> Gt = herm ? cm_negconj<NB>(G) : transpose<NB>(L, G, tb);
+  const CM<NB> Yt = transpose<NB>(L, Y, tb);
+  const CM<NB> G2 = mul_nt<NB>(G, Gt);
+  CM<NB> dG2 = mul_nt<NB>(Y, Gt);
+  mul_nt_acc<NB>(G, Yt, dG2);                                     // Y G + G Y
+  const CM<NB> G2t = herm ? cm_conj<NB>(G2) : transpose<NB>(L, G2, tb);
+  const CM<NB> dG2t = transpose<NB>(L, dG2, tb);
+  CM<NB> Y1t = cm_scale<NB>(Gt, T8_X1); cm_axpy<NB>(Y1t, T8_X2, G2t);
+  CM<NB> dY1t = cm_scale<NB>(Yt, T8_X1); cm_axpy<NB>(dY1t, T8_X2, dG2t);
+  const CM<NB> G4 = mul_nt<NB>(G2, Y1t);
+  CM<NB> dG4 = mul_nt<NB>(dG2, Y1t);
+  mul_nt_acc<NB>(G2, dY1t, dG4);                                  // dG2 Y1 + G2 dY1
+  const CM<NB> G4t = transpose<NB>(L, G4, tb);
+  const CM<NB> dG4t = transpose<NB>(L, dG4, tb);
   CM<NB> L8 = G4; cm_axpy<NB>(L8, T8_X3, G2);
-  CM<NB> R8 = cm_scale<NB>(G, T8_X5); cm_axpy<NB>(R8, T8_X6, G2); cm_axpy<NB>(R8, T8_X7, G4);
-  cm_add_identity<NB>(L, R8, T8_X4);
   CM<NB> dL8 = dG4; cm_axpy<NB>(dL8, T8_X3, dG2);
-  CM<NB> dR8 = cm_scale<NB>(Y, T8_X5); cm_axpy<NB>(dR8, T8_X6, dG2); cm_axpy<NB>(dR8, T8_X7, dG4);
-  FA<NB> L8a = to_A<NB>(L, L8);
-  FB<NB> R8b = to_B<NB>(L, R8);
-  CM<NB> dP = mul<NB>(to_A<NB>(L, dL8), R8b);
-  mul_acc<NB>(L8a, to_B<NB>(L, dR8), dP);
-  cm_axpy<NB>(dP, 1.0, Y); cm_axpy<NB>(dP, T8_Y2, dG2);
+  CM<NB> R8t = cm_scale<NB>(Gt, T8_X5); cm_axpy<NB>(R8t, T8_X6, G2t); cm_axpy<NB>(R8t, T8_X7, G4t);
+  cm_add_identity<NB>(L, R8t, T8_X4);
+  CM<NB> dR8t = cm_scale<NB>(Yt, T8_X5); cm_axpy<NB>(dR8t, T8_X6, dG2t); cm_axpy<NB>(dR8t, T8_X7, dG4t);
+  CM<NB> dP = Y; cm_axpy<NB>(dP, T8_Y2, dG2);
+  mul_nt_acc<NB>(dL8, R8t, dP);
+  mul_nt_acc<NB>(L8, dR8t, dP);                                   // dL8 R8 + L8 dR8 + Y + y2 dG2
   if (s) {
-    CM<NB> P = mul<NB>(L8a, R8b);
-    cm_axpy<NB>(P, 1.0, G); cm_axpy<NB>(P, T8_Y2, G2); cm_add_identity<NB>(L, P, 1.0);
+    CM<NB> P = G; cm_axpy<NB>(P, T8_Y2, G2); cm_add_identity<NB>(L, P, 1.0);
+    mul_nt_acc<NB>(L8, R8t, P);
     for (int j = 0; j < s; j++) {
-      FA<NB> Pa = to_A<NB>(L, P);
-      FB<NB> Pb = to_B<NB>(L, P);
-      CM<NB> nd = mul<NB>(to_A<NB>(L, dP), Pb);
-      mul_acc<NB>(Pa, to_B<NB>(L, dP), nd);
+      const CM<NB> Pt = transpose<NB>(L, P, tb);
+      const CM<NB> dPt = transpose<NB>(L, dP, tb);
+      CM<NB> nd = mul_nt<NB>(dP, Pt);
+      mul_nt_acc<NB>(P, dPt, nd);                                 // dP P + P dP
       dP = nd;
-      if (j + 1 < s) P = mul<NB>(Pa, Pb);
+      if (j + 1 < s) P = mul_nt<NB>(P, Pt);
     }
   }
   return dP;
 }
 
-// G_t = -i*dt*(A + sum_j x[j,t] B_j); packed system matrices: index 0 = A, 1..K = B_j.
-template <int NB>
-__device__ __forceinline__ CM<NB> assemble_generator(const Lane& L, const double2* sysw, const double* xt, int K, double dt) {
-  CM<NB> H = cm_load<NB>(L, sysw);
-  for (int j = 0; j < K; j++) {
-    double xj = __ldg(xt + j);
-    CM<NB> B = cm_load<NB>(L, sysw + (size_t)(j + 1) * cm_elems<NB>());
-    cm_axpy<NB>(H, xj, B);
-  }
-  CM<NB> G;
-  QOC_FOR_CM(NB) { G.re[i][j][e] = dt * H.im[i][j][e]; G.im[i][j][e] = -dt * H.re[i][j][e]; }
+// G_t = A~ + sum_j x[j,t] B~_j with the packed system matrices pre-multiplied by -i*dt on upload
+// (index 0 = A~, 1..K = B~_j), so the generator needs no further scaling.
+constexpr int XPF = 8;   // controls whose amplitudes are prefetched into registers one slice ahead
+template <int NB, bool SH>
+__device__ __forceinline__ CM<NB> assemble_generator(const Lane& L, const double2* sysw, const double* xt, int K,
+                                                     const double* xpre = nullptr) {
+  CM<NB> G = cm_load_sys<NB, SH>(L, sysw);
+#pragma unroll
+  for (int j = 0; j < XPF; j++)
+    if (j < K) cm_axpy_packed<NB, SH>(L, G, xpre ? xpre[j] : __ldg(xt + j), sysw + (size_t)(j + 1) * cm_elems<NB>());
+  for (int j = XPF; j < K; j++) cm_axpy_packed<NB, SH>(L, G, __ldg(xt + j), sysw + (size_t)(j + 1) * cm_elems<NB>());
   return G;
 }
 
 // Which (pulse, member) does this lane's row block belong to.
 template <int CPW> struct Slot {
   int r, k, sysgroup; bool valid;
-  __device__ __forceinline__ Slot(const SmallParams& p, const Lane& L, int w) {
+  __device__ __forceinline__ Slot(int pack_mode, int n_inner, int M, int R, const Lane& L, int w) {
     int s = (CPW == 1) ? 0 : (L.g / (8 / CPW));
-    int outer = w / p.n_inner, inner = w - outer * p.n_inner;
-    if (p.pack_mode == 0) { r = outer; k = inner * CPW + s; sysgroup = inner; valid = k < p.M; if (!valid) k = p.M - 1; }
-    else { k = inner; r = outer * CPW + s; sysgroup = inner; valid = r < p.R; if (!valid) r = p.R - 1; }
+    int outer = w / n_inner, inner = w - outer * n_inner;
+    if (pack_mode == 0) { r = outer; k = inner * CPW + s; sysgroup = inner; valid = k < M; if (!valid) k = M - 1; }
+    else { k = inner; r = outer * CPW + s; sysgroup = inner; valid = r < R; if (!valid) r = R - 1; }
   }
 };
 
-// write the 8-chunked, group-reduced gradient values of slice t
-template <int NB, int CPW>
+// write the 8-chunked, group-reduced gradient values of slice t: out[c] = Re sum mats_c .* W
+template <int NB, int CPW, bool SH>
 __device__ __forceinline__ void emit_gradient(const SmallParams& p, const Lane& L, const Slot<CPW>& sl,
                                               const double2* mats, const CM<NB>& W, int t) {
   constexpr int GS = 32 / CPW;
@@ -172,7 +183,7 @@ __device__ __forceinline__ void emit_gradient(const SmallParams& p, const Lane& 
     double v[8];
 #pragma unroll
     for (int c = 0; c < 8; c++)
-      v[c] = (c0 + c < p.K) ? cm_redot_partial<NB>(L, mats + (size_t)(c0 + c) * cm_elems<NB>(), W) : 0.0;
+      v[c] = (c0 + c < p.K) ? cm_redot_partial<NB, SH>(L, mats + (size_t)(c0 + c) * cm_elems<NB>(), W) : 0.0;
     group_sum8<GS>(L.lane, v);
     int within = L.lane % GS;
     int idx = (within * 8) / GS;
@@ -180,59 +191,91 @@ __device__ __forceinline__ void emit_gradient(const SmallParams& p, const Lane& 
   }
 }
 
+// element (row, col) of the chain this lane's block belongs to, or row = -1 if the element is padding
+template <int NB, int CPW> __device__ __forceinline__ void chain_coords(const Lane& L, int i, int j, int e, int D, int& row, int& col) {
+  constexpr int DPc = 8 * NB / CPW;
+  const int s = (CPW == 1) ? 0 : (L.g / DPc);
+  row = 8 * i + L.g - s * DPc; col = 8 * j + 2 * L.q + e - s * DPc;
+  if (row < 0 || col < 0 || row >= D || col >= D || col >= DPc) row = -1;
+}
+
 // One warp = one packed group of chains; forward sweep (+ expm), figure of merit, backward sweep + gradient.
-template <int NB, int CPW, int SYS, int GRAD>
-__global__ void __launch_bounds__(128) chain_kernel(const SmallParams p) {
-  extern __shared__ double2 smem[];
+// Stored per slice: the TRANSPOSED propagator Pt = P_t^T (what the backward recursions consume) and the state
+// in the polarity its chain runs in (unitary: S_t^T, density: S_t).
+//   unitary forward   S_{t+1}^T = S_t^T P_t^T                = nt(St, P)
+//   density forward   S_{t+1}   = P (S P')                    = nt(P, X),  X = conj(P) S^T = nt(conj P, S)
+//   unitary backward  C_t^T     = C_{t+1}^T conj(P)           = nt(Ct, conj Pt)
+//   density backward  C_t       = P' (C P)                    = nt(conj Pt, Z),  Z = P^T C^T = nt(Pt, C)
+// The scalar factor of the gradient formula is folded into the initial costate (everything is linear in C),
+// next-slice operands (x, Pt, St) are prefetched one iteration ahead so HBM latency overlaps the DMMA work.
+template <int NB, int CPW, int SYS, int GRAD, bool SH>
+__device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) {
   const int warp_in_cta = threadIdx.x >> 5;
   const int w = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
   if (w >= p.n_groups) return;
   const Lane L(threadIdx.x & 31);
-  const Slot<CPW> sl(p, L, w);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   constexpr int GS = 32 / CPW;
   constexpr int E = cm_elems<NB>();
+  constexpr int TBW = NB * NB * 2 * TB_PLANE;                     // doubles of transpose tile per warp
   const float theta = (float)p.theta;
+  const bool herm = p.herm;
+  const int K = p.K, N = p.N;
 
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)warp_in_cta * TBW;
   const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
-  if (p.sys_in_smem) {
-    double2* mine = smem + (size_t)warp_in_cta * p.nmat * E;
+  if (SH) {
+    double2* mine = smem + (size_t)(blockDim.x >> 5) * TBW / 2 + (size_t)warp_in_cta * p.nmat * E;
     for (int i = L.lane; i < p.nmat * E; i += 32) mine[i] = sysw[i];
     __syncwarp();
     sysw = mine;
   }
-  const double* xr = p.x + (size_t)sl.r * p.N * p.K;
-  double2* stP = p.storeP + (size_t)w * p.N * E;
-  double2* stS = p.storeS + (size_t)w * p.N * E;
+  const double* xr = p.x + (size_t)sl.r * N * K;
+  double2* stP = p.storeP + (size_t)w * N * E;
+  double2* stS = p.storeS + (size_t)w * N * E;
   const double invD2 = 1.0 / ((double)p.D * (double)p.D);
+  double xpre[XPF];
+  auto prefetch_x = [&](int t) {
+#pragma unroll
+    for (int j = 0; j < XPF; j++) xpre[j] = (j < K) ? __ldg(xr + (size_t)t * K + j) : 0.0;
+  };
 
-  // ---------------- forward sweep: S_{t+1} = P_t S_t  or  P_t S_t P_t' ----------------
+  // ---------------- forward sweep ----------------
+  // unitary: S holds S_t^T (xi packed transposed); density: S holds S_t
   CM<NB> S = cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E);
-  for (int t = 0; t < p.N; t++) {
+  CM<NB> Pnext;
+  if (p.have_P) Pnext = cm_load<NB>(L, stP); else prefetch_x(0);
+  for (int t = 0; t < N; t++) {
     CM<NB> P;
-    if (p.have_P) P = cm_load<NB>(L, stP + (size_t)t * E);
-    else {
-      P = expm_t8<NB>(L, assemble_generator<NB>(L, sysw, xr + (size_t)t * p.K, p.K, p.dt), theta);
-      if (GRAD != GRAD_NONE) cm_store<NB>(L, stP + (size_t)t * E, P);
+    if (p.have_P) {
+      const CM<NB> Ptl = Pnext;
+      if (t + 1 < N) Pnext = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
+      P = transpose<NB>(L, Ptl, tb);
+    } else {
+      const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
+      if (t + 1 < N) prefetch_x(t + 1);
+      P = expm_t8<NB>(L, G, theta, herm, tb);
+      if (GRAD != GRAD_NONE) cm_store<NB>(L, stP + (size_t)t * E, transpose<NB>(L, P, tb));
     }
     if (GRAD != GRAD_NONE) cm_store<NB>(L, stS + (size_t)t * E, S);
-    FA<NB> Pa = to_A<NB>(L, P);
     if (SYS == SYS_UNITARY) {
-      S = mul<NB>(Pa, to_B<NB>(L, S));
+      S = mul_nt<NB>(S, P);                                       // S^T P^T          (GRAPE.jl:226)
     } else {
-      CM<NB> tmp = mul<NB>(to_A<NB>(L, S), adjB<NB>(Pa));      // S_t P_t'      (GRAPE.jl:245)
-      S = mul<NB>(Pa, to_B<NB>(L, tmp));                          // P_t (S_t P_t') (GRAPE.jl:246)
+      const CM<NB> X = mul_nt<NB, true, false>(P, S);             // conj(P) S^T = (S P')^T   (GRAPE.jl:245)
+      S = mul_nt<NB>(P, X);                                       // P (S P')         (GRAPE.jl:246)
     }
   }
-  CM<NB> Xt = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
+  // xt packed transposed for unitary, so elementwise overlaps with S are consistent in both cases
+  const CM<NB> Xt = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
 
   if (p.out_final) {   // final forward state in the caller's column-major layout (pw_evolve with U0 = Xi)
-    constexpr int DPc = 8 * NB / CPW;
-    int s = (CPW == 1) ? 0 : (L.g / DPc);
     double2* o = p.out_final + ((size_t)sl.r * p.M + sl.k) * p.D * p.D;
     QOC_FOR_CM(NB) {
-      int row = 8 * i + L.g - s * DPc, col = 8 * j + 2 * L.q + e - s * DPc;
-      if (sl.valid && row >= 0 && col >= 0 && row < p.D && col < p.D && col < DPc)
-        o[(size_t)col * p.D + row] = make_double2(S.re[i][j][e], S.im[i][j][e]);
+      int row, col; chain_coords<NB, CPW>(L, i, j, e, p.D, row, col);
+      if (sl.valid && row >= 0) {
+        if (SYS == SYS_UNITARY) o[(size_t)row * p.D + col] = make_double2(S.re[i][j][e], S.im[i][j][e]);   // S holds S^T
+        else o[(size_t)col * p.D + row] = make_double2(S.re[i][j][e], S.im[i][j][e]);
+      }
     }
   }
 
@@ -249,78 +292,83 @@ __global__ void __launch_bounds__(128) chain_kernel(const SmallParams p) {
   if (GRAD == GRAD_NONE) return;
 
   // ---------------- backward sweep + gradient ----------------
-  const double2* Bmats = sysw + E;                        // B_1..B_K
-  const double2* BTmats = sysw + (size_t)(1 + p.K) * E;   // transposed controls (exact mode only)
-  CM<NB> C = Xt;
+  // Trace-dots run against the packed B~_c = -i dt B_c, i.e. B_c = (i/dt) B~_c.  With that factor folded in:
+  //   first order, unitary:  f = 2(+-i dt) tau (i/dt) = -+2 tau          density:  f = (i dt)(i/dt) = -1
+  //   exact, unitary:        f = -(2/D^2) conj(tau) (-i dt)(i/dt) = -(2/D^2) conj(tau)   density: f = -2/D^2
+  // and f W(C) = W(conj(f) C): the costate chain starts from conj(f) Xt.
+  const double2* Bmats = sysw + E;                        // B~_1..B~_K
+  const double2* BTmats = sysw + (size_t)(1 + K) * E;     // transposed controls (exact mode only)
+  CM<NB> C;                                               // unitary: C^T, density: C
   if (GRAD == GRAD_FIRST) {
-    double fr, fi;
-    if (SYS == SYS_UNITARY) { double sg = 2.0 * p.sign_static * p.dt; fr = -sg * ti_; fi = sg * tr_; }   // 2(+-i dt) tau
-    else { fr = 0.0; fi = p.dt; }                                                                       // i dt
-    FB<NB> Cb = to_B<NB>(L, C);
-    FA<NB> Ca = to_A<NB>(L, C);
-    for (int t = p.N - 1; t >= 0; t--) {
-      CM<NB> P = cm_load<NB>(L, stP + (size_t)t * E);
-      CM<NB> St = cm_load<NB>(L, stS + (size_t)t * E);
-      FB<NB> Pb = to_B<NB>(L, P);
+    if (SYS == SYS_UNITARY) { const double sg = -2.0 * p.sign_static; C = cm_cscale<NB>(Xt, sg * tr_, -sg * ti_); }
+    else C = cm_neg<NB>(Xt);
+  } else {
+    const double k2 = 2.0 * invD2;
+    if (SYS == SYS_UNITARY) C = cm_cscale<NB>(Xt, -k2 * tr_, -k2 * ti_);     // conj(-(2/D^2) conj(tau)) = -(2/D^2) tau
+    else C = cm_scale<NB>(Xt, -k2);
+  }
+  CM<NB> Pt_n = cm_load<NB>(L, stP + (size_t)(N - 1) * E);
+  CM<NB> St_n = cm_load<NB>(L, stS + (size_t)(N - 1) * E);
+  if (GRAD == GRAD_EXACT) prefetch_x(N - 1);
+  for (int t = N - 1; t >= 0; t--) {
+    const CM<NB> Pt = Pt_n;
+    const CM<NB> St = St_n;
+    if (t > 0) { Pt_n = cm_load<NB>(L, stP + (size_t)(t - 1) * E); St_n = cm_load<NB>(L, stS + (size_t)(t - 1) * E); }
+    if (GRAD == GRAD_FIRST) {
+      CM<NB> WT;
       if (SYS == SYS_UNITARY) {
-        C = mul<NB>(adjA<NB>(Pb), Cb);                          // C_t = P_t' C_{t+1}      (GRAPE.jl:228)
+        C = mul_nt<NB, false, true>(C, Pt);                       // C_t^T = C_{t+1}^T conj(P)   (GRAPE.jl:228)
+        const CM<NB> Sn = transpose<NB>(L, St, tb);               // S_t
+        const CM<NB> Cn = transpose<NB>(L, C, tb);                // C_t
+        WT = mul_nt<NB, true, false>(Cn, Sn);                     // conj(C) S^T = (S C')^T
       } else {
-        CM<NB> tmp = mul<NB>(Ca, Pb);                           // C_{t+1} P_t             (GRAPE.jl:248)
-        C = mul<NB>(adjA<NB>(Pb), to_B<NB>(L, tmp));            // P_t' (C_{t+1} P_t)      (GRAPE.jl:249)
+        const CM<NB> Z = mul_nt<NB>(Pt, C);                       // P^T C^T = (C P)^T           (GRAPE.jl:248)
+        C = mul_nt<NB, true, false>(Pt, Z);                       // P' (C P)                    (GRAPE.jl:249)
+        const CM<NB> Stt = transpose<NB>(L, St, tb);              // S_t^T
+        const CM<NB> Ctt = transpose<NB>(L, C, tb);               // C_t^T
+        WT = mul_nt<NB, true, false>(C, St);                      // conj(C) S^T = (S C')^T
+        mul_nt_acc<NB, false, true>(cm_neg<NB>(Stt), Ctt, WT);    // - S^T conj(C) = -(C' S)^T
       }
-      Ca = to_A<NB>(L, C);
-      Cb = to_B<NB>(L, C);
-      FA<NB> Sa = to_A<NB>(L, St);
-      // W^T with W = S_t C_t' (unitary) or S_t C_t' - C_t' S_t (density): tr(B W) = sum B .* W^T
-      CM<NB> WT = mul<NB>(conjF<NB>(Ca), trB<NB>(Sa));          // (S C')^T = conj(C) S^T
-      if (SYS == SYS_DENSITY) {
-        FB<NB> Sb = to_B<NB>(L, St);
-        CM<NB> W2 = mul<NB>(trA<NB>(Sb), conjF<NB>(Cb));        // (C' S)^T = S^T conj(C)
-        cm_sub<NB>(WT, W2);
-      }
-      CM<NB> Ws = cm_cscale<NB>(WT, fr, fi);
-      emit_gradient<NB, CPW>(p, L, sl, Bmats, Ws, t);
-    }
-  } else {   // GRAD_EXACT: F = 1 - |tau|^2/D^2, tau = tr(Xt' S_N); dF/dx[c,t] = -(2/D^2) Re(conj(tau) dtau)
-    const double kr = 2.0 * p.dt * invD2;
-    for (int t = p.N - 1; t >= 0; t--) {
-      CM<NB> P = cm_load<NB>(L, stP + (size_t)t * E);
-      CM<NB> St = cm_load<NB>(L, stS + (size_t)t * E);
-      FB<NB> Pb = to_B<NB>(L, P);
-      FA<NB> Sa = to_A<NB>(L, St);
-      FA<NB> Ca = to_A<NB>(L, C);
-      FB<NB> Cb = to_B<NB>(L, C);
-      CM<NB> Y, Cn;
-      double cr, ci;
+      emit_gradient<NB, CPW, SH>(p, L, sl, Bmats, WT, t);         // tr(B W) = sum B .* W^T
+    } else {   // exact: F = 1 - |tau|^2/D^2, dF/dx[c,t] = -(2/D^2) Re(conj(tau) dtau), dtau = tr(Y L(G, -i dt B_c))
+      CM<NB> Y;
       if (SYS == SYS_UNITARY) {
-        Y = mul<NB>(Sa, adjB<NB>(Ca));                          // Y = S_t C_{t+1}'
-        Cn = mul<NB>(adjA<NB>(Pb), Cb);                         // C_t = P_t' C_{t+1}
-        cr = kr * ti_; ci = kr * tr_;                           // -(2/D^2) conj(tau) (-i dt)
+        const CM<NB> Sn = transpose<NB>(L, St, tb);               // S_t
+        const CM<NB> Cn = transpose<NB>(L, C, tb);                // C_{t+1}
+        Y = mul_nt<NB, false, true>(Sn, Cn);                      // Y = S_t C_{t+1}'
+        C = mul_nt<NB, false, true>(C, Pt);                       // C_t^T
       } else {
-        FA<NB> Pda = adjA<NB>(Pb);
-        CM<NB> Q1 = mul<NB>(Pda, adjB<NB>(Ca));                 // P_t' C_{t+1}'
-        CM<NB> Q2 = mul<NB>(Pda, Cb);                           // P_t' C_{t+1}
-        FB<NB> Sb = to_B<NB>(L, St);
-        CM<NB> Y1 = mul<NB>(Sa, to_B<NB>(L, Q1));               // S_t P_t' C_{t+1}'
-        CM<NB> Y2 = mul<NB>(adjA<NB>(Sb), to_B<NB>(L, Q2));     // S_t' P_t' C_{t+1}
-        Y = cm_cscale<NB>(Y1, tr_, -ti_);                       // conj(tau) Y1 + tau Y2
+        const CM<NB> Ctt = transpose<NB>(L, C, tb);               // C_{t+1}^T
+        const CM<NB> Stt = transpose<NB>(L, St, tb);              // S_t^T
+        const CM<NB> A1t = mul_nt<NB, true, true>(C, Pt);         // conj(C) conj(P) = (P' C')^T
+        const CM<NB> A2t = mul_nt<NB, false, true>(Ctt, Pt);      // C^T conj(P)     = (P' C)^T
+        const CM<NB> Y1 = mul_nt<NB>(St, A1t);                    // S P' C'
+        const CM<NB> Y2 = mul_nt<NB, true, false>(Stt, A2t);      // S' P' C
+        Y = cm_cscale<NB>(Y1, tr_, -ti_);                         // conj(tau) Y1 + tau Y2
         cm_caxpy<NB>(Y, tr_, ti_, Y2);
-        Cn = mul<NB>(to_A<NB>(L, Q2), Pb);                      // C_t = P_t' C_{t+1} P_t
-        cr = 0.0; ci = kr;                                      // -(2/D^2)(-i dt)
+        const CM<NB> Z = mul_nt<NB>(Pt, C);                       // (C P)^T
+        C = mul_nt<NB, true, false>(Pt, Z);                       // C_t = P' C P
       }
-      CM<NB> G = assemble_generator<NB>(L, sysw, xr + (size_t)t * p.K, p.K, p.dt);
-      CM<NB> Lam = frechet_t8<NB>(L, G, Y, theta);
-      CM<NB> Ws = cm_cscale<NB>(Lam, cr, ci);
-      emit_gradient<NB, CPW>(p, L, sl, BTmats, Ws, t);          // tr(Lam B_c) = sum Lam .* B_c^T
-      C = Cn;
+      const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
+      if (t > 0) prefetch_x(t - 1);
+      const CM<NB> Lam = frechet_t8<NB>(L, G, Y, theta, herm, tb);
+      emit_gradient<NB, CPW, SH>(p, L, sl, BTmats, Lam, t);       // tr(Lam B_c) = sum Lam .* B_c^T
     }
   }
 }
 
-// Slice-parallel propagators: one warp per (system group / pulse, slice).  Writes the packed layout used by
-// chain_kernel (storeP) and/or the caller's column-major layout (pw_prop_save!, timeevolution.jl:98-110).
+template <int NB, int CPW, int SYS, int GRAD>
+__global__ void __launch_bounds__(128) chain_kernel(const SmallParams p) {
+  extern __shared__ double2 smem[];
+  if (p.sys_in_smem) chain_body<NB, CPW, SYS, GRAD, true>(p, smem);
+  else chain_body<NB, CPW, SYS, GRAD, false>(p, smem);
+}
+
+// Slice-parallel propagators: one warp per (system group / pulse, slice).  Writes the packed TRANSPOSED
+// propagator used by chain_kernel (storeP) and/or the caller's column-major layout
+// (pw_prop_save!, timeevolution.jl:98-110).
 struct SliceParams {
-  int D, N, K, M, R, pack_mode, n_groups, n_inner, nmat;
+  int D, N, K, M, R, pack_mode, n_groups, n_inner, nmat, herm;
   double dt, theta;
   const double2* sys;
   const double* x;
@@ -330,31 +378,25 @@ struct SliceParams {
 };
 template <int NB, int CPW>
 __global__ void __launch_bounds__(128) expm_slices_kernel(const SliceParams p) {
+  extern __shared__ double2 smem[];
   const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= (long)p.n_groups * p.N) return;
   const int w = (int)(gw / p.N), t = (int)(gw - (long)w * p.N);
   const Lane L(threadIdx.x & 31);
-  SmallParams sp; sp.M = p.M; sp.R = p.R; sp.pack_mode = p.pack_mode; sp.n_inner = p.n_inner;
-  const Slot<CPW> sl(sp, L, w);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   constexpr int E = cm_elems<NB>();
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
   const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
   const double* xt = p.x + ((size_t)sl.r * p.N + t) * p.K;
-  CM<NB> out;
-  if (p.mode == 0) out = expm_t8<NB>(L, assemble_generator<NB>(L, sysw, xt, p.K, p.dt), (float)p.theta);
-  else if (p.mode == 2) out = assemble_generator<NB>(L, sysw, xt, p.K, p.dt);
-  else {  // H = i/dt * G  (undo the -i dt factor exactly: re = -G.im/dt ... computed directly instead)
-    out = cm_load<NB>(L, sysw);
-    for (int j = 0; j < p.K; j++) cm_axpy<NB>(out, __ldg(xt + j), cm_load<NB>(L, sysw + (size_t)(j + 1) * E));
-  }
-  if (p.storeP) cm_store<NB>(L, p.storeP + ((size_t)w * p.N + t) * E, out);
+  CM<NB> out = assemble_generator<NB, false>(L, sysw, xt, p.K);                // G = -i dt H
+  if (p.mode == 0) out = expm_t8<NB>(L, out, (float)p.theta, p.herm, tb);
+  else if (p.mode == 1) out = cm_cscale<NB>(out, 0.0, 1.0 / p.dt);            // H = (i/dt) G
+  if (p.storeP) cm_store<NB>(L, p.storeP + ((size_t)w * p.N + t) * E, transpose<NB>(L, out, tb));
   if (p.out_user) {
-    constexpr int DPc = 8 * NB / CPW;
-    int s = (CPW == 1) ? 0 : (L.g / DPc);
     double2* o = p.out_user + (((size_t)sl.r * p.M + sl.k) * p.N + t) * p.D * p.D;
     QOC_FOR_CM(NB) {
-      int row = 8 * i + L.g - s * DPc, col = 8 * j + 2 * L.q + e - s * DPc;
-      if (sl.valid && row >= 0 && col >= 0 && row < p.D && col < p.D && col < DPc)
-        o[(size_t)col * p.D + row] = make_double2(out.re[i][j][e], out.im[i][j][e]);
+      int row, col; chain_coords<NB, CPW>(L, i, j, e, p.D, row, col);
+      if (sl.valid && row >= 0) o[(size_t)col * p.D + row] = make_double2(out.re[i][j][e], out.im[i][j][e]);
     }
   }
 }
@@ -367,6 +409,7 @@ struct PackParams {
   int pack_mode;      // 0: slot s -> member og*CPW+s (clamped to n_src-1); 1: every slot -> member og
   int n_src;          // number of distinct source matrices (1 if shared)
   long src_stride;    // in double2 between consecutive source members (0 if shared)
+  double scale_re, scale_im;   // every element is multiplied by this complex factor (-i*dt for A, B)
   const double2* src;
   double2* dst;
 };
@@ -390,7 +433,7 @@ __global__ void pack_kernel(const PackParams p) {
       if (member > p.n_src - 1) member = p.n_src - 1;
       const double2* m = p.src + member * p.src_stride;
       double2 z = p.transpose ? m[(size_t)rr * p.D + cc] : m[(size_t)cc * p.D + rr];
-      val = ri ? z.y : z.x;
+      val = ri ? (p.scale_re * z.y + p.scale_im * z.x) : (p.scale_re * z.x - p.scale_im * z.y);
     }
     v[e] = val;
   }
@@ -402,10 +445,12 @@ __global__ void pack_kernel(const PackParams p) {
 __global__ void reduce_members_pass1(const double* __restrict__ gradc, const double* __restrict__ fomc,
                                      const double* __restrict__ wts, double* __restrict__ part,
                                      int M, int NK, int chunk, int nchunks) {
-  // grid: (ceil((NK+1)/256), nchunks, R); part[r][chunk][NK+1] (entry 0 = fom)
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  // grid: (ceil((NK+1)/256) * R, nchunks); part[r][chunk][NK+1] (entry 0 = fom)
+  const int bpr = (NK + 1 + blockDim.x - 1) / blockDim.x;
+  int r = blockIdx.x / bpr;
+  int e = (blockIdx.x - r * bpr) * blockDim.x + threadIdx.x;
   if (e > NK) return;
-  int ch = blockIdx.y, r = blockIdx.z;
+  int ch = blockIdx.y;
   int k0 = ch * chunk, k1 = min(M, k0 + chunk);
   double s = 0.0;
   if (e == 0) { for (int k = k0; k < k1; k++) s += wts[k] * fomc[(size_t)r * M + k]; }
@@ -413,9 +458,10 @@ __global__ void reduce_members_pass1(const double* __restrict__ gradc, const dou
   part[((size_t)r * nchunks + ch) * (NK + 1) + e] = s;
 }
 __global__ void reduce_members_pass2(const double* __restrict__ part, double* __restrict__ out, int NK, int nchunks) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bpr = (NK + 1 + blockDim.x - 1) / blockDim.x;
+  int r = blockIdx.x / bpr;
+  int e = (blockIdx.x - r * bpr) * blockDim.x + threadIdx.x;
   if (e > NK) return;
-  int r = blockIdx.y;
   double s = 0.0;
   for (int ch = 0; ch < nchunks; ch++) s += part[((size_t)r * nchunks + ch) * (NK + 1) + e];
   out[(size_t)r * (NK + 1) + e] = s;

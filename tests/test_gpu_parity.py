@@ -164,3 +164,15 @@ def test_errors_are_loud():
             ev.eval(np.zeros((3, 5)))
     with pytest.raises(qoc.QocError):
         qoc.GrapeEvaluator([(A, B, Xi, Xt)], 1.0, 0, orc.STATE_TRANSFER)
+
+
+def test_huge_multistart_batch():
+    """R > 65535 pulses in one call (grid-dimension limits) — spot-check a few against the oracle."""
+    D, K, N, T, R = 2, 2, 3, 1.0, 70001
+    A, B, Xi, Xt = random_system(D, K, seed=77)
+    xs = np.random.default_rng(0).uniform(-1, 1, (R, K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER, n_pulses=R) as ev:
+        F, G = ev.eval(xs)
+    for r in (0, 1, 2, 3, 65535, 65536, R - 2, R - 1):
+        Fo, Go = orc.fom_and_gradient_grape(A, B, xs[r], T, Xi, Xt, orc.STATE_TRANSFER)
+        assert_parity(F[r], G[r], Fo, Go)
