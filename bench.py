@@ -56,7 +56,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -146,7 +146,7 @@ def run_reference(args, cfg, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="cfg4")
     ap.add_argument("--pulses", type=int, default=0, help="multi-start pulses per step (0 = config default)")
@@ -217,11 +217,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # started early: nvidia-smi needs ~0.1 s to come up
     for _ in range(args.warmup):
         step_device()
     barrier()
     ev.stats()                                    # reset the kernel-event ring
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start = time.perf_counter()
     e0.record(stream)

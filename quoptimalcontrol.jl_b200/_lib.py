@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqocgrape.so")
+LIB_PATH = os.environ.get("QOCGRAPE_LIB") or os.path.join(HERE, "libqocgrape.so")   # env override: tuning builds
 
 QOC_OK, QOC_EINVAL, QOC_ECUDA, QOC_ENOMEM, QOC_EUNSUPPORTED = 0, 1, 2, 3, 4
 STATE_TRANSFER, UNITARY_GATE, COHERENCE_TRANSFER = 0, 1, 2

@@ -2,11 +2,14 @@
 // entry point either runs the sm_100a kernels or returns an error.
 #include "../../include/qocgrape.h"
 #include "small_d.cuh"
+#include "small_phased.cuh"
 #include "big_d.cuh"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -24,7 +27,9 @@ struct qoc_handle {
   int kring_count = 0;
   // derived small-path geometry
   int path = 0, NB = 1, CPW = 1, pack_mode = 0, n_groups = 0, n_inner = 0, n_sysgroups = 0, nmat = 0;
-  int have_P = 0, sys_in_smem = 0, smem_bytes = 0, tb_bytes = 0, herm = 0;
+  int have_P = 0, sys_in_smem = 0, smem_bytes = 0, tb_bytes = 0, herm = 0, phased = 0, Cn = 1;
+  double2 *storeP2 = nullptr, *stS = nullptr, *stC = nullptr, *totT = nullptr, *totTt = nullptr;
+  double* tau = nullptr;
   int NK = 0, red_chunk = 0, red_nchunks = 0;
   bool system_set = false;
   // device buffers
@@ -131,7 +136,19 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     if (h->pack_mode == 0) { h->n_inner = (d.M + h->CPW - 1) / h->CPW; h->n_groups = d.R * h->n_inner; h->n_sysgroups = h->n_inner; }
     else { h->n_inner = d.M; h->n_groups = ((d.R + h->CPW - 1) / h->CPW) * d.M; h->n_sysgroups = d.M; }
     h->nmat = 1 + d.K + (d.gradient == QOC_GRAD_EXACT ? d.K : 0);
-    h->have_P = h->n_groups < 148 * 8;   // too few chains to fill the GPU: exponentials go slice-parallel
+    // Execution strategy (measured on cfg4 shards, profiles/README.md): below ~800 chains one warp per chain cannot
+    // fill 592 warp schedulers -> chunked prefix scan over slices (small_phased.cuh); short pulses stay fused.
+    h->phased = h->n_groups < 800 && d.N >= 32;
+    if (const char* e = getenv("QOC_PHASED")) h->phased = atoi(e) != 0;
+    h->have_P = h->phased;               // slice-parallel exponentials feed the value-only path as well
+    if (const char* e = getenv("QOC_HAVE_P")) h->have_P = atoi(e) != 0;   // tuning override
+    if (h->phased) {
+      h->have_P = 1;
+      int want = (592 + 2 * h->n_groups - 1) / (2 * h->n_groups);        // sweep warps >= one per SM sub-partition
+      int cap = (int)std::sqrt((double)d.N);                              // depth L + Cn is minimal near sqrt(N)
+      h->Cn = std::max(1, std::min(std::min(want, cap), d.N / 2 > 0 ? d.N / 2 : 1));
+      if (const char* e = getenv("QOC_CHUNKS")) h->Cn = std::max(1, std::min(atoi(e), d.N));
+    }
     const size_t E = (size_t)h->NB * h->NB * 64;
     h->tb_bytes = 4 * h->NB * h->NB * 2 * TB_PLANE * (int)sizeof(double);     // per-warp transpose tiles
     size_t smem = (size_t)4 * h->nmat * E * sizeof(double2);
@@ -142,7 +159,15 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     CR(dev_alloc(h, &h->xt, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->ident, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->storeP, (size_t)h->n_groups * d.N * E));
-    CR(dev_alloc(h, &h->storeS, (size_t)h->n_groups * d.N * E));
+    if (!h->phased) CR(dev_alloc(h, &h->storeS, (size_t)h->n_groups * d.N * E));
+    if (h->phased) {
+      CR(dev_alloc(h, &h->storeP2, (size_t)h->n_groups * d.N * E));
+      CR(dev_alloc(h, &h->stS, (size_t)h->n_groups * (d.N + 1) * E));
+      CR(dev_alloc(h, &h->stC, (size_t)h->n_groups * (d.N + 1) * E));
+      CR(dev_alloc(h, &h->totT, (size_t)h->n_groups * h->Cn * E));
+      CR(dev_alloc(h, &h->totTt, (size_t)h->n_groups * h->Cn * E));
+      CR(dev_alloc(h, &h->tau, (size_t)h->n_groups * h->CPW * 2));
+    }
     CR(dev_alloc(h, &h->fomc, (size_t)d.R * d.M));
     CR(dev_alloc(h, &h->gradc, (size_t)d.R * d.M * h->NK));
   } else {
@@ -173,7 +198,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->big) big_destroy(h->big);
-  void* bufs[] = {h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
+  void* bufs[] = {h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hout) cudaFreeHost(h->hout);
@@ -294,7 +319,7 @@ static SliceParams slice_params(qoc_handle* h, const double* x_dev) {
   SliceParams s;
   s.D = d.D; s.N = d.N; s.K = d.K; s.M = d.M; s.R = d.R; s.pack_mode = h->pack_mode; s.n_groups = h->n_groups;
   s.n_inner = h->n_inner; s.nmat = h->nmat; s.herm = h->herm; s.dt = d.T / d.N; s.theta = d.expm_theta;
-  s.sys = h->sys; s.x = x_dev; s.storeP = nullptr; s.out_user = nullptr; s.mode = 0;
+  s.sys = h->sys; s.x = x_dev; s.storeP = nullptr; s.storeP2 = nullptr; s.out_user = nullptr; s.mode = 0;
   return s;
 }
 static int launch_chain(qoc_handle* h, const SmallParams& p, int sys, int grad, cudaStream_t st) {
@@ -310,6 +335,49 @@ static int launch_slices(qoc_handle* h, const SliceParams& s, cudaStream_t st) {
   return launch_check(h, "expm_slices_kernel");
 }
 
+// dispatch of the phased-pipeline kernels
+typedef void (*phased_fn)(const PhasedParams);
+template <int NB, int CPW> static void pick_phased(int sys, int grad, phased_fn& tot, phased_fn& bnd, phased_fn& swp, phased_fn& grd) {
+  tot = chunk_totals_kernel<NB, CPW>;
+  if (sys == SYS_UNITARY) {
+    bnd = boundary_kernel<NB, CPW, SYS_UNITARY>; swp = sweep_kernel<NB, CPW, SYS_UNITARY>;
+    grd = grad == GRAD_EXACT ? grad_slices_kernel<NB, CPW, SYS_UNITARY, GRAD_EXACT> : grad_slices_kernel<NB, CPW, SYS_UNITARY, GRAD_FIRST>;
+  } else {
+    bnd = boundary_kernel<NB, CPW, SYS_DENSITY>; swp = sweep_kernel<NB, CPW, SYS_DENSITY>;
+    grd = grad == GRAD_EXACT ? grad_slices_kernel<NB, CPW, SYS_DENSITY, GRAD_EXACT> : grad_slices_kernel<NB, CPW, SYS_DENSITY, GRAD_FIRST>;
+  }
+}
+
+static int eval_phased(qoc_handle* h, const double* x_dev, int sys, int grad, cudaStream_t st) {
+  const qoc_desc& d = h->d;
+  int rc;
+  SliceParams s = slice_params(h, x_dev);
+  s.storeP = h->storeP; s.storeP2 = h->storeP2;
+  if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
+  PhasedParams p;
+  p.D = d.D; p.N = d.N; p.K = d.K; p.M = d.M; p.R = d.R; p.pack_mode = h->pack_mode; p.n_groups = h->n_groups; p.n_inner = h->n_inner;
+  p.nmat = h->nmat; p.herm = h->herm; p.Cn = h->Cn; p.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1;
+  p.fom_exact = d.gradient == QOC_GRAD_EXACT; p.theta = d.expm_theta;
+  p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev; p.storePt = h->storeP; p.storeP = h->storeP2; p.stS = h->stS; p.stC = h->stC;
+  p.totT = h->totT; p.totTt = h->totTt; p.tau = h->tau; p.fomc = h->fomc; p.gradc = h->gradc;
+  phased_fn tot, bnd, swp, grd;
+  if (h->NB == 2) pick_phased<2, 1>(sys, grad, tot, bnd, swp, grd);
+  else if (h->CPW == 4) pick_phased<1, 4>(sys, grad, tot, bnd, swp, grd);
+  else if (h->CPW == 2) pick_phased<1, 2>(sys, grad, tot, bnd, swp, grd);
+  else pick_phased<1, 1>(sys, grad, tot, bnd, swp, grd);
+  auto blocks = [](long warps) { return (unsigned)((warps + 3) / 4); };
+  if (h->Cn > 1) {
+    tot<<<blocks((long)h->n_groups * h->Cn), 128, h->tb_bytes, st>>>(p);
+    if ((rc = launch_check(h, "chunk_totals_kernel")) != QOC_OK) return rc;
+  }
+  bnd<<<blocks((long)h->n_groups * 2), 128, 0, st>>>(p);
+  if ((rc = launch_check(h, "boundary_kernel")) != QOC_OK) return rc;
+  swp<<<blocks((long)h->n_groups * h->Cn * 2), 128, 0, st>>>(p);
+  if ((rc = launch_check(h, "sweep_kernel")) != QOC_OK) return rc;
+  grd<<<blocks((long)h->n_groups * d.N), 128, h->tb_bytes, st>>>(p);
+  return launch_check(h, "grad_slices_kernel");
+}
+
 static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int want_grad, cudaStream_t st) {
   const qoc_desc& d = h->d;
   int rc;
@@ -318,12 +386,16 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   const int grad = !want_grad ? GRAD_NONE : (d.gradient == QOC_GRAD_EXACT ? GRAD_EXACT : GRAD_FIRST);
   const int slot = h->kring_count % qoc_handle::KRING;
   QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
-  if (h->have_P) {
-    SliceParams s = slice_params(h, x_dev);
-    s.storeP = h->storeP;
-    if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
+  if (h->phased && want_grad) {
+    if ((rc = eval_phased(h, x_dev, sys, grad, st)) != QOC_OK) return rc;
+  } else {
+    if (h->have_P) {
+      SliceParams s = slice_params(h, x_dev);
+      s.storeP = h->storeP;
+      if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
+    }
+    if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
   }
-  if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
   QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st));
   h->kring_count++;
   dim3 g1((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R), h->red_nchunks);

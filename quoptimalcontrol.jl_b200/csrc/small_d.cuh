@@ -357,8 +357,12 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
   }
 }
 
+// 5 CTAs/SM -> 96 registers, 20 warps/SM: best of {4,5,6,7} on cfg4 (6 and 7 spill; see profiles/README.md)
+#ifndef QOC_CHAIN_MINB
+#define QOC_CHAIN_MINB 5
+#endif
 template <int NB, int CPW, int SYS, int GRAD>
-__global__ void __launch_bounds__(128) chain_kernel(const SmallParams p) {
+__global__ void __launch_bounds__(128, (NB == 1 && GRAD != GRAD_EXACT) ? QOC_CHAIN_MINB : 1) chain_kernel(const SmallParams p) {
   extern __shared__ double2 smem[];
   if (p.sys_in_smem) chain_body<NB, CPW, SYS, GRAD, true>(p, smem);
   else chain_body<NB, CPW, SYS, GRAD, false>(p, smem);
@@ -372,7 +376,8 @@ struct SliceParams {
   double dt, theta;
   const double2* sys;
   const double* x;
-  double2* storeP;     // optional packed [n_groups][N][E]
+  double2* storeP;     // optional packed [n_groups][N][E]: TRANSPOSED result
+  double2* storeP2;    // optional packed [n_groups][N][E]: result as is
   double2* out_user;   // optional [R][M][N][D*D] column-major complex
   int mode;            // 0: propagator exp(-i dt H); 1: Hamiltonian H (pw_ham_save!); 2: generator -i dt H (pw_gen_save!)
 };
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(128) expm_slices_kernel(const SliceParams p) {
   if (p.mode == 0) out = expm_t8<NB>(L, out, (float)p.theta, p.herm, tb);
   else if (p.mode == 1) out = cm_cscale<NB>(out, 0.0, 1.0 / p.dt);            // H = (i/dt) G
   if (p.storeP) cm_store<NB>(L, p.storeP + ((size_t)w * p.N + t) * E, transpose<NB>(L, out, tb));
+  if (p.storeP2) cm_store<NB>(L, p.storeP2 + ((size_t)w * p.N + t) * E, out);
   if (p.out_user) {
     double2* o = p.out_user + (((size_t)sl.r * p.M + sl.k) * p.N + t) * p.D * p.D;
     QOC_FOR_CM(NB) {

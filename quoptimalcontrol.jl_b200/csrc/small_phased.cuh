@@ -1,0 +1,233 @@
+// Low-batch ("phased") small-D pipeline: when there are too few (pulse, member) chains to fill 148 SMs with one
+// warp per chain, the slice axis supplies the parallelism.  A chunked three-level prefix scan over slices replaces
+// the sequential sweeps of /root/reference/src/GRAPE.jl:53-75:
+//   A  expm_slices_kernel      P_t for every (group, slice)                         [slice-parallel]
+//   B1 chunk_totals_kernel     T_c = P_{t1-1} ... P_{t0} for every (group, chunk)   [chunk-parallel, L-1 products]
+//   B2 boundary_kernel         S[start_c], C[start_c] through the T_c               [Cn sequential steps per group]
+//   B3 sweep_kernel            forward and backward sweeps inside every chunk, concurrently, storing S_t, C_t
+//   C  grad_slices_kernel      W_t (or the Frechet derivative for the exact gradient) + K trace-dots per slice
+//                              [slice-parallel]  -- grad_func!, /root/reference/src/GRAPE.jl:261-287
+// With Cn = 1 (B1/B2 skipped) this is plain slice-parallel expm/gradient around two sequential sweep warps per chain.
+#pragma once
+#include "small_d.cuh"
+
+namespace qoc {
+
+struct PhasedParams {
+  int D, N, K, M, R, pack_mode, n_groups, n_inner, nmat, herm, Cn;
+  int sign_static, fom_exact;
+  double theta;
+  const double2* sys;      // packed, pre-multiplied by -i dt
+  const double2* xi;       // packed (unitary: transposed)
+  const double2* xt;
+  const double* x;
+  double2* storePt;        // [n_groups][N][E]   P_t^T
+  double2* storeP;         // [n_groups][N][E]   P_t
+  double2* stS;            // [n_groups][N+1][E] unitary: S_t^T, density: S_t
+  double2* stC;            // [n_groups][N+1][E] unitary: C_t^T, density: C_t   (C_N = Xt)
+  double2* totT;           // [n_groups][Cn][E]  T_c
+  double2* totTt;          // [n_groups][Cn][E]  T_c^T
+  double* tau;             // [n_groups][CPW][2] overlap per chain (written by the forward sweep)
+  double* fomc;
+  double* gradc;
+};
+
+__device__ __forceinline__ int chunk_lo(int c, int N, int Cn) { return (int)((long)c * N / Cn); }
+
+// B1: chunk-total propagators.  T <- T * P_t for t descending: nt(T, Pt) = T * (P_t^T)^T, no transposes needed.
+template <int NB, int CPW>
+__global__ void __launch_bounds__(128) chunk_totals_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= p.n_groups * p.Cn) return;
+  const int w = gw / p.Cn, c = gw - w * p.Cn;
+  const Lane L(threadIdx.x & 31);
+  constexpr int E = cm_elems<NB>();
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
+  const int t0 = chunk_lo(c, p.N, p.Cn), t1 = chunk_lo(c + 1, p.N, p.Cn);
+  const double2* Pt = p.storePt + (size_t)w * p.N * E;
+  CM<NB> T = cm_load<NB>(L, p.storeP + ((size_t)w * p.N + (t1 - 1)) * E);
+  CM<NB> nxt;
+  if (t1 - 2 >= t0) nxt = cm_load<NB>(L, Pt + (size_t)(t1 - 2) * E);
+  for (int t = t1 - 2; t >= t0; t--) {
+    const CM<NB> cur = nxt;
+    if (t - 1 >= t0) nxt = cm_load<NB>(L, Pt + (size_t)(t - 1) * E);
+    T = mul_nt<NB>(T, cur);
+  }
+  cm_store<NB>(L, p.totT + ((size_t)w * p.Cn + c) * E, T);
+  cm_store<NB>(L, p.totTt + ((size_t)w * p.Cn + c) * E, transpose<NB>(L, T, tb));
+}
+
+// B2: boundary states / costates.  Warp 2w: forward over chunks; warp 2w+1: backward.
+template <int NB, int CPW, int SYS>
+__global__ void __launch_bounds__(128) boundary_kernel(const PhasedParams p) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= p.n_groups * 2) return;
+  const int w = gw >> 1, dir = gw & 1;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int E = cm_elems<NB>();
+  const int N = p.N, Cn = p.Cn;
+  if (dir == 0) {
+    CM<NB> S = cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E);
+    double2* st = p.stS + (size_t)w * (N + 1) * E;
+    cm_store<NB>(L, st, S);
+    for (int c = 0; c < Cn - 1; c++) {       // the last boundary (S_N) is produced by the sweep itself
+      const CM<NB> T = cm_load<NB>(L, p.totT + ((size_t)w * Cn + c) * E);
+      if (SYS == SYS_UNITARY) S = mul_nt<NB>(S, T);
+      else { const CM<NB> X = mul_nt<NB, true, false>(T, S); S = mul_nt<NB>(T, X); }
+      cm_store<NB>(L, st + (size_t)chunk_lo(c + 1, N, Cn) * E, S);
+    }
+  } else {
+    CM<NB> C = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
+    double2* st = p.stC + (size_t)w * (N + 1) * E;
+    cm_store<NB>(L, st + (size_t)N * E, C);
+    for (int c = Cn - 1; c >= 1; c--) {
+      const CM<NB> Tt = cm_load<NB>(L, p.totTt + ((size_t)w * Cn + c) * E);
+      if (SYS == SYS_UNITARY) C = mul_nt<NB, false, true>(C, Tt);
+      else { const CM<NB> Z = mul_nt<NB>(Tt, C); C = mul_nt<NB, true, false>(Tt, Z); }
+      cm_store<NB>(L, st + (size_t)chunk_lo(c, N, Cn) * E, C);
+    }
+  }
+}
+
+// B3: within-chunk sweeps.  Warp index = ((w * Cn + c) * 2 + dir).  Forward reads P, backward reads P^T; both
+// prefetch two slices ahead (an iteration is shorter than DRAM latency).
+template <int NB, int CPW, int SYS>
+__global__ void __launch_bounds__(128) sweep_kernel(const PhasedParams p) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= p.n_groups * p.Cn * 2) return;
+  const int dir = gw & 1, rest = gw >> 1;
+  const int w = rest / p.Cn, c = rest - w * p.Cn;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int GS = 32 / CPW;
+  constexpr int E = cm_elems<NB>();
+  const int N = p.N, Cn = p.Cn;
+  const int t0 = chunk_lo(c, N, Cn), t1 = chunk_lo(c + 1, N, Cn);
+  constexpr int PF = 4;     // prefetch ring depth: a sweep step is far shorter than DRAM latency
+  if (dir == 0) {
+    const double2* Pm = p.storeP + (size_t)w * N * E;
+    double2* st = p.stS + (size_t)w * (N + 1) * E;
+    CM<NB> S = cm_load<NB>(L, st + (size_t)t0 * E);
+    CM<NB> ring[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) if (t0 + i < t1) ring[i] = cm_load<NB>(L, Pm + (size_t)(t0 + i) * E);
+    for (int tb0 = t0; tb0 < t1; tb0 += PF) {
+#pragma unroll
+      for (int i = 0; i < PF; i++) {
+        const int t = tb0 + i;
+        if (t < t1) {
+          const CM<NB> P = ring[i];
+          if (t + PF < t1) ring[i] = cm_load<NB>(L, Pm + (size_t)(t + PF) * E);
+          if (SYS == SYS_UNITARY) S = mul_nt<NB>(S, P);
+          else { const CM<NB> X = mul_nt<NB, true, false>(P, S); S = mul_nt<NB>(P, X); }
+          if (t + 1 < t1 || c == Cn - 1) cm_store<NB>(L, st + (size_t)(t + 1) * E, S);
+        }
+      }
+    }
+    if (c == Cn - 1) {      // S holds the final state: overlap and figure of merit (cost_functions.jl:99-111)
+      const CM<NB> Xt = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
+      double tr_, ti_;
+      const bool ref_unitary_fom = SYS == SYS_UNITARY && !p.fom_exact;
+      if (ref_unitary_fom) cm_dotc_partial<NB>(S, Xt, tr_, ti_); else cm_dotc_partial<NB>(Xt, S, tr_, ti_);
+      tr_ = group_sum<GS>(tr_); ti_ = group_sum<GS>(ti_);
+      const double invD2 = 1.0 / ((double)p.D * (double)p.D);
+      const double fom = ref_unitary_fom ? tr_ * tr_ - ti_ * ti_ : 1.0 - (tr_ * tr_ + ti_ * ti_) * invD2;
+      if ((L.lane % GS) == 0) {
+        const int s = L.lane / GS;
+        p.tau[((size_t)w * CPW + s) * 2 + 0] = tr_; p.tau[((size_t)w * CPW + s) * 2 + 1] = ti_;
+        if (sl.valid) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
+      }
+    }
+  } else {
+    const double2* Pm = p.storePt + (size_t)w * N * E;
+    double2* st = p.stC + (size_t)w * (N + 1) * E;
+    CM<NB> C = cm_load<NB>(L, st + (size_t)t1 * E);
+    CM<NB> ring[PF];
+#pragma unroll
+    for (int i = 0; i < PF; i++) if (t1 - 1 - i >= t0) ring[i] = cm_load<NB>(L, Pm + (size_t)(t1 - 1 - i) * E);
+    for (int tb0 = t1 - 1; tb0 >= t0; tb0 -= PF) {
+#pragma unroll
+      for (int i = 0; i < PF; i++) {
+        const int t = tb0 - i;
+        if (t >= t0) {
+          const CM<NB> Pt = ring[i];
+          if (t - PF >= t0) ring[i] = cm_load<NB>(L, Pm + (size_t)(t - PF) * E);
+          if (SYS == SYS_UNITARY) C = mul_nt<NB, false, true>(C, Pt);
+          else { const CM<NB> Z = mul_nt<NB>(Pt, C); C = mul_nt<NB, true, false>(Pt, Z); }
+          if (t > t0 || c == 0) cm_store<NB>(L, st + (size_t)t * E, C);
+        }
+      }
+    }
+  }
+}
+
+// C: gradient of every (group, slice).  Same formulas and factors as chain_body's backward loop.
+template <int NB, int CPW, int SYS, int GRAD>
+__global__ void __launch_bounds__(128) grad_slices_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  const long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (long)p.n_groups * p.N) return;
+  const int w = (int)(gw / p.N), t = (int)(gw - (long)w * p.N);
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int GS = 32 / CPW;
+  constexpr int E = cm_elems<NB>();
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
+  const int N = p.N, K = p.K;
+  const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
+  const double2* Bmats = sysw + E;
+  const double2* BTmats = sysw + (size_t)(1 + K) * E;
+  const int slot = L.lane / GS;
+  const double tr_ = p.tau[((size_t)w * CPW + slot) * 2 + 0], ti_ = p.tau[((size_t)w * CPW + slot) * 2 + 1];
+  const double invD2 = 1.0 / ((double)p.D * (double)p.D);
+  const double2* stS = p.stS + (size_t)w * (N + 1) * E;
+  const double2* stC = p.stC + (size_t)w * (N + 1) * E;
+  SmallParams sp;   // only the fields emit_gradient reads
+  sp.M = p.M; sp.N = N; sp.K = K; sp.gradc = p.gradc;
+  if (GRAD == GRAD_FIRST) {
+    const CM<NB> St = cm_load<NB>(L, stS + (size_t)t * E);
+    const CM<NB> Ct = cm_load<NB>(L, stC + (size_t)t * E);
+    CM<NB> WT;
+    double fr, fi;
+    if (SYS == SYS_UNITARY) {
+      const CM<NB> Sn = transpose<NB>(L, St, tb), Cn = transpose<NB>(L, Ct, tb);
+      WT = mul_nt<NB, true, false>(Cn, Sn);
+      const double sg = -2.0 * p.sign_static; fr = sg * tr_; fi = sg * ti_;
+    } else {
+      const CM<NB> Stt = transpose<NB>(L, St, tb), Ctt = transpose<NB>(L, Ct, tb);
+      WT = mul_nt<NB, true, false>(Ct, St);
+      mul_nt_acc<NB, false, true>(cm_neg<NB>(Stt), Ctt, WT);
+      fr = -1.0; fi = 0.0;
+    }
+    emit_gradient<NB, CPW, false>(sp, L, sl, Bmats, cm_cscale<NB>(WT, fr, fi), t);
+  } else {
+    const double k2 = 2.0 * invD2;
+    const CM<NB> St = cm_load<NB>(L, stS + (size_t)t * E);
+    const CM<NB> C1 = cm_load<NB>(L, stC + (size_t)(t + 1) * E);      // costate after slice t
+    CM<NB> Y;
+    double cr, ci;
+    if (SYS == SYS_UNITARY) {
+      const CM<NB> Sn = transpose<NB>(L, St, tb), Cn = transpose<NB>(L, C1, tb);
+      Y = mul_nt<NB, false, true>(Sn, Cn);
+      cr = -k2 * tr_; ci = k2 * ti_;
+    } else {
+      const CM<NB> Pt = cm_load<NB>(L, p.storePt + ((size_t)w * N + t) * E);
+      const CM<NB> Ctt = transpose<NB>(L, C1, tb), Stt = transpose<NB>(L, St, tb);
+      const CM<NB> A1t = mul_nt<NB, true, true>(C1, Pt);
+      const CM<NB> A2t = mul_nt<NB, false, true>(Ctt, Pt);
+      const CM<NB> Y1 = mul_nt<NB>(St, A1t);
+      const CM<NB> Y2 = mul_nt<NB, true, false>(Stt, A2t);
+      Y = cm_cscale<NB>(Y1, tr_, -ti_);
+      cm_caxpy<NB>(Y, tr_, ti_, Y2);
+      cr = -k2; ci = 0.0;
+    }
+    const double* xr = p.x + ((size_t)sl.r * N + t) * K;
+    const CM<NB> G = assemble_generator<NB, false>(L, sysw, xr, K);
+    const CM<NB> Lam = frechet_t8<NB>(L, G, Y, (float)p.theta, p.herm, tb);
+    emit_gradient<NB, CPW, false>(sp, L, sl, BTmats, cm_cscale<NB>(Lam, cr, ci), t);
+  }
+}
+
+}  // namespace qoc

@@ -176,3 +176,27 @@ def test_huge_multistart_batch():
     for r in (0, 1, 2, 3, 65535, 65536, R - 2, R - 1):
         Fo, Go = orc.fom_and_gradient_grape(A, B, xs[r], T, Xi, Xt, orc.STATE_TRANSFER)
         assert_parity(F[r], G[r], Fo, Go)
+
+
+@pytest.mark.parametrize("env", [{"QOC_PHASED": "1", "QOC_CHUNKS": "1"}, {"QOC_PHASED": "1", "QOC_CHUNKS": "4"},
+                                 {"QOC_PHASED": "0"}, {"QOC_PHASED": "0", "QOC_HAVE_P": "0"}])
+@pytest.mark.parametrize("D,sys_name,gradient", [(8, "unitary", "first_order"), (4, "state", "first_order"),
+                                                 (16, "coherence", "first_order"), (4, "unitary", "exact"),
+                                                 (8, "state", "exact"), (2, "state", "first_order")])
+def test_pipeline_modes(monkeypatch, env, D, sys_name, gradient):
+    """Every execution strategy (fused warp-per-chain, slice-parallel exponentials, chunked prefix scan over
+    slices with 1 or several chunks) must give the same numbers."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    K, N, T, M = 3, 13, 1.1, 3
+    members = [random_system(D, K, seed=900 + D + k, hermitian=(sys_name != "coherence"),
+                             unitary_targets=(sys_name == "unitary")) for k in range(M)]
+    wts = [0.2, 0.5, 0.3]
+    x = np.random.default_rng(D).uniform(-1, 1, (K, N))
+    F, G, F0 = _run(members, wts, T, N, SYS[sys_name], x, gradient)
+    if gradient == "exact":
+        Fo, Go = orc.ensemble_exact(members, wts, x, T, SYS[sys_name])
+    else:
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, x, T, SYS[sys_name])
+    assert_parity(F, G, Fo, Go)
+    assert_parity(F0, None, Fo, None)
