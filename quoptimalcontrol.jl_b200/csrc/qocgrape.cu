@@ -30,6 +30,8 @@ struct qoc_handle {
   int have_P = 0, sys_in_smem = 0, smem_bytes = 0, tb_bytes = 0, herm = 0, phased = 0, Cn = 1;
   double2 *storeP2 = nullptr, *stS = nullptr, *stC = nullptr, *totT = nullptr, *totTt = nullptr;
   double* tau = nullptr;
+  int chunked = 0;                       // chunk-parallel fused mode (150..1500 chains)
+  double2 *bS = nullptr, *bC = nullptr;
   int NK = 0, red_chunk = 0, red_nchunks = 0;
   bool system_set = false;
   // device buffers
@@ -136,12 +138,22 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     if (h->pack_mode == 0) { h->n_inner = (d.M + h->CPW - 1) / h->CPW; h->n_groups = d.R * h->n_inner; h->n_sysgroups = h->n_inner; }
     else { h->n_inner = d.M; h->n_groups = ((d.R + h->CPW - 1) / h->CPW) * d.M; h->n_sysgroups = d.M; }
     h->nmat = 1 + d.K + (d.gradient == QOC_GRAD_EXACT ? d.K : 0);
-    // Execution strategy (measured on cfg4 shards, profiles/README.md): below ~800 chains one warp per chain cannot
-    // fill 592 warp schedulers -> chunked prefix scan over slices (small_phased.cuh); short pulses stay fused.
-    h->phased = h->n_groups < 800 && d.N >= 32;
-    if (const char* e = getenv("QOC_PHASED")) h->phased = atoi(e) != 0;
+    // Execution strategy (thresholds measured on cfg4 shards, profiles/README.md):
+    //   >= 1500 chains        fused chain_kernel, one warp per chain
+    //   150..1499 chains      chunk-parallel fused: each chain split into Cn chunks (full occupancy)
+    //   < 150 chains          fully slice-parallel pipeline with a chunked prefix scan (small_phased.cuh)
+    // Short pulses stay on the plain fused kernel.
+    h->phased = h->n_groups < 150 && d.N >= 32;
+    h->chunked = !h->phased && h->n_groups < 1500 && d.N >= 64;
+    if (const char* e = getenv("QOC_PHASED")) { h->phased = atoi(e) != 0; if (h->phased) h->chunked = 0; }
+    if (const char* e = getenv("QOC_CHUNKED")) { h->chunked = atoi(e) != 0; if (h->chunked) h->phased = 0; }
     h->have_P = h->phased;               // slice-parallel exponentials feed the value-only path as well
     if (const char* e = getenv("QOC_HAVE_P")) h->have_P = atoi(e) != 0;   // tuning override
+    if (h->chunked) {
+      h->have_P = 0;
+      h->Cn = std::max(2, std::min((8192 + h->n_groups - 1) / h->n_groups, std::max(2, d.N / 16)));   // ~8192 warps measured best
+      if (const char* e = getenv("QOC_CHUNKS")) h->Cn = std::max(2, std::min(atoi(e), d.N));
+    }
     if (h->phased) {
       h->have_P = 1;
       int want = (592 + 2 * h->n_groups - 1) / (2 * h->n_groups);        // sweep warps >= one per SM sub-partition
@@ -160,6 +172,13 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     CR(dev_alloc(h, &h->ident, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->storeP, (size_t)h->n_groups * d.N * E));
     if (!h->phased) CR(dev_alloc(h, &h->storeS, (size_t)h->n_groups * d.N * E));
+    if (h->chunked) {
+      CR(dev_alloc(h, &h->totT, (size_t)h->n_groups * h->Cn * E));
+      CR(dev_alloc(h, &h->totTt, (size_t)h->n_groups * h->Cn * E));
+      CR(dev_alloc(h, &h->bS, (size_t)h->n_groups * (h->Cn + 1) * E));
+      CR(dev_alloc(h, &h->bC, (size_t)h->n_groups * (h->Cn + 1) * E));
+      CR(dev_alloc(h, &h->tau, (size_t)h->n_groups * h->CPW * 2));
+    }
     if (h->phased) {
       CR(dev_alloc(h, &h->storeP2, (size_t)h->n_groups * d.N * E));
       CR(dev_alloc(h, &h->stS, (size_t)h->n_groups * (d.N + 1) * E));
@@ -198,7 +217,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->big) big_destroy(h->big);
-  void* bufs[] = {h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
+  void* bufs[] = {h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hout) cudaFreeHost(h->hout);
@@ -312,6 +331,7 @@ static SmallParams small_params(qoc_handle* h, const double* x_dev) {
   p.dt = d.T / d.N; p.theta = d.expm_theta;
   p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev;
   p.storeP = h->storeP; p.storeS = h->storeS; p.fomc = h->fomc; p.gradc = h->gradc; p.out_final = nullptr;
+  p.Cn = 1; p.bS = nullptr; p.bC = nullptr; p.tau_in = nullptr;
   return p;
 }
 static SliceParams slice_params(qoc_handle* h, const double* x_dev) {
@@ -326,13 +346,25 @@ static int launch_chain(qoc_handle* h, const SmallParams& p, int sys, int grad, 
   chain_fn fn = pick_chain(h->NB, h->CPW, sys, grad);
   if (h->smem_bytes > 48 * 1024)
     QOC_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-  fn<<<(unsigned)((h->n_groups + 3) / 4), 128, h->smem_bytes, st>>>(p);
+  fn<<<(unsigned)(((long)h->n_groups * (p.Cn > 1 ? p.Cn : 1) + 3) / 4), 128, h->smem_bytes, st>>>(p);
   return launch_check(h, "chain_kernel");
 }
 static int launch_slices(qoc_handle* h, const SliceParams& s, cudaStream_t st) {
   long warps = (long)h->n_groups * h->d.N;
   pick_slices(h->NB, h->CPW)<<<(unsigned)((warps + 3) / 4), 128, h->tb_bytes, st>>>(s);
   return launch_check(h, "expm_slices_kernel");
+}
+
+static PhasedParams phased_params(qoc_handle* h, const double* x_dev) {
+  const qoc_desc& d = h->d;
+  PhasedParams p;
+  p.D = d.D; p.N = d.N; p.K = d.K; p.M = d.M; p.R = d.R; p.pack_mode = h->pack_mode; p.n_groups = h->n_groups; p.n_inner = h->n_inner;
+  p.nmat = h->nmat; p.herm = h->herm; p.Cn = h->Cn; p.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1;
+  p.fom_exact = d.gradient == QOC_GRAD_EXACT; p.theta = d.expm_theta;
+  p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev; p.storePt = h->storeP; p.storeP = h->storeP2; p.stS = h->stS; p.stC = h->stC;
+  p.totT = h->totT; p.totTt = h->totTt; p.tau = h->tau; p.fomc = h->fomc; p.gradc = h->gradc;
+  p.bS = h->bS; p.bC = h->bC; p.sys_in_smem = 0;
+  return p;
 }
 
 // dispatch of the phased-pipeline kernels
@@ -354,12 +386,7 @@ static int eval_phased(qoc_handle* h, const double* x_dev, int sys, int grad, cu
   SliceParams s = slice_params(h, x_dev);
   s.storeP = h->storeP; s.storeP2 = h->storeP2;
   if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
-  PhasedParams p;
-  p.D = d.D; p.N = d.N; p.K = d.K; p.M = d.M; p.R = d.R; p.pack_mode = h->pack_mode; p.n_groups = h->n_groups; p.n_inner = h->n_inner;
-  p.nmat = h->nmat; p.herm = h->herm; p.Cn = h->Cn; p.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1;
-  p.fom_exact = d.gradient == QOC_GRAD_EXACT; p.theta = d.expm_theta;
-  p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev; p.storePt = h->storeP; p.storeP = h->storeP2; p.stS = h->stS; p.stC = h->stC;
-  p.totT = h->totT; p.totTt = h->totTt; p.tau = h->tau; p.fomc = h->fomc; p.gradc = h->gradc;
+  PhasedParams p = phased_params(h, x_dev);
   phased_fn tot, bnd, swp, grd;
   if (h->NB == 2) pick_phased<2, 1>(sys, grad, tot, bnd, swp, grd);
   else if (h->CPW == 4) pick_phased<1, 4>(sys, grad, tot, bnd, swp, grd);
@@ -378,6 +405,29 @@ static int eval_phased(qoc_handle* h, const double* x_dev, int sys, int grad, cu
   return launch_check(h, "grad_slices_kernel");
 }
 
+// chunk-parallel fused mode: exponentials + chunk totals, boundary states, then the fused body per chunk
+static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int sys, int grad, cudaStream_t st) {
+  int rc;
+  PhasedParams p = phased_params(h, x_dev);
+  const size_t E = (size_t)h->NB * h->NB * 64;
+  const size_t sys_bytes = (size_t)4 * (1 + h->d.K) * E * sizeof(double2);
+  p.sys_in_smem = sys_bytes + h->tb_bytes <= 96 * 1024;
+  const int smem1 = h->tb_bytes + (p.sys_in_smem ? (int)sys_bytes : 0);
+  typedef void (*kfn)(const PhasedParams);
+  kfn k1, k2;
+  if (h->NB == 2) { k1 = chunk_expm_kernel<2, 1>; k2 = sys == SYS_UNITARY ? boundary2_kernel<2, 1, SYS_UNITARY> : boundary2_kernel<2, 1, SYS_DENSITY>; }
+  else if (h->CPW == 4) { k1 = chunk_expm_kernel<1, 4>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 4, SYS_UNITARY> : boundary2_kernel<1, 4, SYS_DENSITY>; }
+  else if (h->CPW == 2) { k1 = chunk_expm_kernel<1, 2>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 2, SYS_UNITARY> : boundary2_kernel<1, 2, SYS_DENSITY>; }
+  else { k1 = chunk_expm_kernel<1, 1>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 1, SYS_UNITARY> : boundary2_kernel<1, 1, SYS_DENSITY>; }
+  if (smem1 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+  k1<<<(unsigned)(((long)h->n_groups * h->Cn + 3) / 4), 128, smem1, st>>>(p);
+  if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
+  k2<<<(unsigned)((h->n_groups * 2 + 3) / 4), 128, 0, st>>>(p);
+  if ((rc = launch_check(h, "boundary2_kernel")) != QOC_OK) return rc;
+  cp.Cn = h->Cn; cp.bS = h->bS; cp.bC = h->bC; cp.tau_in = h->tau; cp.have_P = 1;
+  return launch_chain(h, cp, sys, grad, st);
+}
+
 static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int want_grad, cudaStream_t st) {
   const qoc_desc& d = h->d;
   int rc;
@@ -388,6 +438,8 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if (h->phased && want_grad) {
     if ((rc = eval_phased(h, x_dev, sys, grad, st)) != QOC_OK) return rc;
+  } else if (h->chunked && want_grad) {
+    if ((rc = eval_chunked(h, p, x_dev, sys, grad, st)) != QOC_OK) return rc;
   } else {
     if (h->have_P) {
       SliceParams s = slice_params(h, x_dev);

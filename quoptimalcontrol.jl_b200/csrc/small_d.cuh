@@ -48,6 +48,12 @@ struct SmallParams {
   double* fomc;        // [R][M]
   double* gradc;       // [R][M][N][K]
   double2* out_final;  // optional [R][M][D*D]: final forward state, column-major complex
+  // chunk-parallel fused mode (Cn > 1): warp (w, c) handles slices [c*N/Cn, (c+1)*N/Cn) of group w, starting from
+  // the boundary state bS[w][c] and boundary costate bC[w][c+1]; overlaps come from tau_in (boundary2_kernel)
+  int Cn;
+  const double2* bS;   // [n_groups][Cn+1][E]
+  const double2* bC;   // [n_groups][Cn+1][E]
+  const double* tau_in;  // [n_groups][CPW][2]
 };
 
 template <int NB> __host__ __device__ constexpr int cm_elems() { return NB * NB * 2 * 32; }  // double2 per packed matrix
@@ -211,8 +217,11 @@ template <int NB, int CPW> __device__ __forceinline__ void chain_coords(const La
 template <int NB, int CPW, int SYS, int GRAD, bool SH>
 __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) {
   const int warp_in_cta = threadIdx.x >> 5;
-  const int w = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  if (w >= p.n_groups) return;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  const int Cn = p.Cn > 1 ? p.Cn : 1;
+  if (gw >= p.n_groups * Cn) return;
+  const int w = gw / Cn, ck = gw - w * Cn;
+  const bool chunked = Cn > 1;
   const Lane L(threadIdx.x & 31);
   const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   constexpr int GS = 32 / CPW;
@@ -221,6 +230,7 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
   const float theta = (float)p.theta;
   const bool herm = p.herm;
   const int K = p.K, N = p.N;
+  const int t0 = (int)((long)ck * N / Cn), t1 = (int)((long)(ck + 1) * N / Cn);
 
   double* tb = reinterpret_cast<double*>(smem) + (size_t)warp_in_cta * TBW;
   const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
@@ -242,18 +252,18 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
 
   // ---------------- forward sweep ----------------
   // unitary: S holds S_t^T (xi packed transposed); density: S holds S_t
-  CM<NB> S = cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E);
+  CM<NB> S = chunked ? cm_load<NB>(L, p.bS + ((size_t)w * (Cn + 1) + ck) * E) : cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E);
   CM<NB> Pnext;
-  if (p.have_P) Pnext = cm_load<NB>(L, stP); else prefetch_x(0);
-  for (int t = 0; t < N; t++) {
+  if (p.have_P) Pnext = cm_load<NB>(L, stP + (size_t)t0 * E); else prefetch_x(t0);
+  for (int t = t0; t < t1; t++) {
     CM<NB> P;
     if (p.have_P) {
       const CM<NB> Ptl = Pnext;
-      if (t + 1 < N) Pnext = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
+      if (t + 1 < t1) Pnext = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
       P = transpose<NB>(L, Ptl, tb);
     } else {
       const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
-      if (t + 1 < N) prefetch_x(t + 1);
+      if (t + 1 < t1) prefetch_x(t + 1);
       P = expm_t8<NB>(L, G, theta, herm, tb);
       if (GRAD != GRAD_NONE) cm_store<NB>(L, stP + (size_t)t * E, transpose<NB>(L, P, tb));
     }
@@ -268,7 +278,7 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
   // xt packed transposed for unitary, so elementwise overlaps with S are consistent in both cases
   const CM<NB> Xt = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
 
-  if (p.out_final) {   // final forward state in the caller's column-major layout (pw_evolve with U0 = Xi)
+  if (p.out_final && !chunked) {   // final forward state in the caller's column-major layout (pw_evolve with U0 = Xi)
     double2* o = p.out_final + ((size_t)sl.r * p.M + sl.k) * p.D * p.D;
     QOC_FOR_CM(NB) {
       int row, col; chain_coords<NB, CPW>(L, i, j, e, p.D, row, col);
@@ -285,10 +295,15 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
   if (ref_unitary_fom) cm_dotc_partial<NB>(S, Xt, tr_, ti_);                            // tr(S' Xt)
   else cm_dotc_partial<NB>(Xt, S, tr_, ti_);                                            // tr(Xt' S)
   tr_ = group_sum<GS>(tr_); ti_ = group_sum<GS>(ti_);
-  double fom;
-  if (ref_unitary_fom) fom = tr_ * tr_ - ti_ * ti_;                                     // Re(tau*tau)
-  else fom = 1.0 - (tr_ * tr_ + ti_ * ti_) * invD2;                                     // C1
-  if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
+  if (chunked) {      // overlaps and figures of merit were produced by boundary2_kernel from the chunk totals
+    const int slot = L.lane / GS;
+    tr_ = p.tau_in[((size_t)w * CPW + slot) * 2 + 0]; ti_ = p.tau_in[((size_t)w * CPW + slot) * 2 + 1];
+  } else {
+    double fom;
+    if (ref_unitary_fom) fom = tr_ * tr_ - ti_ * ti_;                                   // Re(tau*tau)
+    else fom = 1.0 - (tr_ * tr_ + ti_ * ti_) * invD2;                                   // C1
+    if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
+  }
   if (GRAD == GRAD_NONE) return;
 
   // ---------------- backward sweep + gradient ----------------
@@ -299,21 +314,22 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
   const double2* Bmats = sysw + E;                        // B~_1..B~_K
   const double2* BTmats = sysw + (size_t)(1 + K) * E;     // transposed controls (exact mode only)
   CM<NB> C;                                               // unitary: C^T, density: C
+  const CM<NB> C0 = chunked ? cm_load<NB>(L, p.bC + ((size_t)w * (Cn + 1) + ck + 1) * E) : Xt;   // costate after this chunk
   if (GRAD == GRAD_FIRST) {
-    if (SYS == SYS_UNITARY) { const double sg = -2.0 * p.sign_static; C = cm_cscale<NB>(Xt, sg * tr_, -sg * ti_); }
-    else C = cm_neg<NB>(Xt);
+    if (SYS == SYS_UNITARY) { const double sg = -2.0 * p.sign_static; C = cm_cscale<NB>(C0, sg * tr_, -sg * ti_); }
+    else C = cm_neg<NB>(C0);
   } else {
     const double k2 = 2.0 * invD2;
-    if (SYS == SYS_UNITARY) C = cm_cscale<NB>(Xt, -k2 * tr_, -k2 * ti_);     // conj(-(2/D^2) conj(tau)) = -(2/D^2) tau
-    else C = cm_scale<NB>(Xt, -k2);
+    if (SYS == SYS_UNITARY) C = cm_cscale<NB>(C0, -k2 * tr_, -k2 * ti_);     // conj(-(2/D^2) conj(tau)) = -(2/D^2) tau
+    else C = cm_scale<NB>(C0, -k2);
   }
-  CM<NB> Pt_n = cm_load<NB>(L, stP + (size_t)(N - 1) * E);
-  CM<NB> St_n = cm_load<NB>(L, stS + (size_t)(N - 1) * E);
-  if (GRAD == GRAD_EXACT) prefetch_x(N - 1);
-  for (int t = N - 1; t >= 0; t--) {
+  CM<NB> Pt_n = cm_load<NB>(L, stP + (size_t)(t1 - 1) * E);
+  CM<NB> St_n = cm_load<NB>(L, stS + (size_t)(t1 - 1) * E);
+  if (GRAD == GRAD_EXACT) prefetch_x(t1 - 1);
+  for (int t = t1 - 1; t >= t0; t--) {
     const CM<NB> Pt = Pt_n;
     const CM<NB> St = St_n;
-    if (t > 0) { Pt_n = cm_load<NB>(L, stP + (size_t)(t - 1) * E); St_n = cm_load<NB>(L, stS + (size_t)(t - 1) * E); }
+    if (t > t0) { Pt_n = cm_load<NB>(L, stP + (size_t)(t - 1) * E); St_n = cm_load<NB>(L, stS + (size_t)(t - 1) * E); }
     if (GRAD == GRAD_FIRST) {
       CM<NB> WT;
       if (SYS == SYS_UNITARY) {
@@ -350,7 +366,7 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
         C = mul_nt<NB, true, false>(Pt, Z);                       // C_t = P' C P
       }
       const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
-      if (t > 0) prefetch_x(t - 1);
+      if (t > t0) prefetch_x(t - 1);
       const CM<NB> Lam = frechet_t8<NB>(L, G, Y, theta, herm, tb);
       emit_gradient<NB, CPW, SH>(p, L, sl, BTmats, Lam, t);       // tr(Lam B_c) = sum Lam .* B_c^T
     }

@@ -28,6 +28,9 @@ struct PhasedParams {
   double2* totT;           // [n_groups][Cn][E]  T_c
   double2* totTt;          // [n_groups][Cn][E]  T_c^T
   double* tau;             // [n_groups][CPW][2] overlap per chain (written by the forward sweep)
+  double2* bS;             // [n_groups][Cn+1][E] chunk-boundary states   (chunk-parallel fused mode)
+  double2* bC;             // [n_groups][Cn+1][E] chunk-boundary costates
+  int sys_in_smem;
   double* fomc;
   double* gradc;
 };
@@ -227,6 +230,102 @@ __global__ void __launch_bounds__(128) grad_slices_kernel(const PhasedParams p) 
     const CM<NB> G = assemble_generator<NB, false>(L, sysw, xr, K);
     const CM<NB> Lam = frechet_t8<NB>(L, G, Y, (float)p.theta, p.herm, tb);
     emit_gradient<NB, CPW, false>(sp, L, sl, BTmats, cm_cscale<NB>(Lam, cr, ci), t);
+  }
+}
+
+// ---- chunk-parallel fused mode (150..1500 chains) ------------------------------------------------------
+// K1: warp (w, c): exponentials of the chunk's slices (stored transposed for the later sweeps) and the running
+//     chunk total, T_new^T = T_old^T P_t^T = nt(Tt, P).
+template <int NB, int CPW, bool SH>
+__device__ __forceinline__ void chunk_expm_body(const PhasedParams& p, double2* smem) {
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  if (gw >= p.n_groups * p.Cn) return;
+  const int w = gw / p.Cn, c = gw - w * p.Cn;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int E = cm_elems<NB>();
+  constexpr int TBW = NB * NB * 2 * TB_PLANE;
+  const int N = p.N, K = p.K;
+  const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)warp_in_cta * TBW;
+  const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
+  if (SH) {
+    double2* mine = smem + (size_t)(blockDim.x >> 5) * TBW / 2 + (size_t)warp_in_cta * (1 + K) * E;
+    for (int i = L.lane; i < (1 + K) * E; i += 32) mine[i] = sysw[i];
+    __syncwarp();
+    sysw = mine;
+  }
+  const double* xr = p.x + (size_t)sl.r * N * K;
+  double2* stP = p.storePt + (size_t)w * N * E;
+  double xpre[XPF];
+#pragma unroll
+  for (int j = 0; j < XPF; j++) xpre[j] = (j < K) ? __ldg(xr + (size_t)t0 * K + j) : 0.0;
+  CM<NB> Tt;
+  for (int t = t0; t < t1; t++) {
+    const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int j = 0; j < XPF; j++) xpre[j] = (j < K) ? __ldg(xr + (size_t)(t + 1) * K + j) : 0.0;
+    }
+    const CM<NB> P = expm_t8<NB>(L, G, (float)p.theta, p.herm, tb);
+    const CM<NB> Pt = transpose<NB>(L, P, tb);
+    cm_store<NB>(L, stP + (size_t)t * E, Pt);
+    Tt = (t == t0) ? Pt : mul_nt<NB>(Tt, P);
+  }
+  cm_store<NB>(L, p.totTt + ((size_t)w * p.Cn + c) * E, Tt);
+  cm_store<NB>(L, p.totT + ((size_t)w * p.Cn + c) * E, transpose<NB>(L, Tt, tb));
+}
+template <int NB, int CPW>
+__global__ void __launch_bounds__(128, NB == 1 ? 5 : 1) chunk_expm_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  if (p.sys_in_smem) chunk_expm_body<NB, CPW, true>(p, smem); else chunk_expm_body<NB, CPW, false>(p, smem);
+}
+
+// K2: per group, forward warp: boundary states bS[0..Cn] and the overlap / figure of merit; backward warp: boundary
+// costates bC[Cn..1] (unscaled: chain_body folds the gradient factor in when it loads them).
+template <int NB, int CPW, int SYS>
+__global__ void __launch_bounds__(128) boundary2_kernel(const PhasedParams p) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= p.n_groups * 2) return;
+  const int w = gw >> 1, dir = gw & 1;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int GS = 32 / CPW;
+  constexpr int E = cm_elems<NB>();
+  const int Cn = p.Cn;
+  if (dir == 0) {
+    CM<NB> S = cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E);
+    double2* st = p.bS + (size_t)w * (Cn + 1) * E;
+    cm_store<NB>(L, st, S);
+    for (int c = 0; c < Cn; c++) {
+      const CM<NB> T = cm_load<NB>(L, p.totT + ((size_t)w * Cn + c) * E);
+      if (SYS == SYS_UNITARY) S = mul_nt<NB>(S, T);
+      else { const CM<NB> X = mul_nt<NB, true, false>(T, S); S = mul_nt<NB>(T, X); }
+      cm_store<NB>(L, st + (size_t)(c + 1) * E, S);
+    }
+    const CM<NB> Xt = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
+    double tr_, ti_;
+    const bool ref_unitary_fom = SYS == SYS_UNITARY && !p.fom_exact;
+    if (ref_unitary_fom) cm_dotc_partial<NB>(S, Xt, tr_, ti_); else cm_dotc_partial<NB>(Xt, S, tr_, ti_);
+    tr_ = group_sum<GS>(tr_); ti_ = group_sum<GS>(ti_);
+    const double invD2 = 1.0 / ((double)p.D * (double)p.D);
+    const double fom = ref_unitary_fom ? tr_ * tr_ - ti_ * ti_ : 1.0 - (tr_ * tr_ + ti_ * ti_) * invD2;
+    if ((L.lane % GS) == 0) {
+      const int s = L.lane / GS;
+      p.tau[((size_t)w * CPW + s) * 2 + 0] = tr_; p.tau[((size_t)w * CPW + s) * 2 + 1] = ti_;
+      if (sl.valid) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
+    }
+  } else {
+    CM<NB> C = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
+    double2* st = p.bC + (size_t)w * (Cn + 1) * E;
+    cm_store<NB>(L, st + (size_t)Cn * E, C);
+    for (int c = Cn - 1; c >= 1; c--) {
+      const CM<NB> Tt = cm_load<NB>(L, p.totTt + ((size_t)w * Cn + c) * E);
+      if (SYS == SYS_UNITARY) C = mul_nt<NB, false, true>(C, Tt);
+      else { const CM<NB> Z = mul_nt<NB>(Tt, C); C = mul_nt<NB, true, false>(Tt, Z); }
+      cm_store<NB>(L, st + (size_t)c * E, C);
+    }
   }
 }
 

@@ -179,7 +179,9 @@ def test_huge_multistart_batch():
 
 
 @pytest.mark.parametrize("env", [{"QOC_PHASED": "1", "QOC_CHUNKS": "1"}, {"QOC_PHASED": "1", "QOC_CHUNKS": "4"},
-                                 {"QOC_PHASED": "0"}, {"QOC_PHASED": "0", "QOC_HAVE_P": "0"}])
+                                 {"QOC_PHASED": "0", "QOC_CHUNKED": "0", "QOC_HAVE_P": "1"},
+                                 {"QOC_PHASED": "0", "QOC_CHUNKED": "0", "QOC_HAVE_P": "0"},
+                                 {"QOC_CHUNKED": "1", "QOC_CHUNKS": "2"}, {"QOC_CHUNKED": "1", "QOC_CHUNKS": "5"}])
 @pytest.mark.parametrize("D,sys_name,gradient", [(8, "unitary", "first_order"), (4, "state", "first_order"),
                                                  (16, "coherence", "first_order"), (4, "unitary", "exact"),
                                                  (8, "state", "exact"), (2, "state", "first_order")])
