@@ -15,6 +15,7 @@
 #include <vector>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include "../../include/qocgrape.h"
 #include "zgemm_dmma.cuh"
 
@@ -176,9 +177,10 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
   s->Dp = ((d.D + 63) / 64) * 64;
   s->DD = (size_t)s->Dp * s->Dp;
   s->unitary = d.sys_type == QOC_UNITARY_GATE;
-  // chunking: 16*(Dp/64)^2 ... tiles per GEMM; aim at two full waves of 2 CTAs/SM (592 CTAs) per lock-step launch
+  // chunking: (Dp/64)^2 tiles per GEMM; aim at one full wave of 2 CTAs/SM (296 CTAs) per lock-step launch
   int tiles = (s->Dp / 64) * (s->Dp / 64);
-  int Cn = std::max(1, 592 / tiles);
+  int Cn = std::max(1, 296 / tiles);   // one full wave (2 CTAs/SM) per lock-step launch: measured best of {18, 37, 74} at D = 256
+  if (const char* e = getenv("QOC_BIG_CHUNKS")) Cn = std::max(1, atoi(e));   // tuning override
   Cn = std::min(Cn, std::max(1, d.N / 2));
   s->Cn = Cn;
   s->start.resize(Cn); s->len.resize(Cn);

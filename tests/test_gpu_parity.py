@@ -202,3 +202,20 @@ def test_pipeline_modes(monkeypatch, env, D, sys_name, gradient):
         Fo, Go = orc.ensemble_fom_and_gradient(members, wts, x, T, SYS[sys_name])
     assert_parity(F, G, Fo, Go)
     assert_parity(F0, None, Fo, None)
+
+
+@pytest.mark.parametrize("D,K,N,M,R", [(1, 1, 1, 1, 1), (2, 1, 1, 1, 1), (8, 1, 1, 2, 1), (3, 2, 2, 1, 3), (16, 1, 1, 1, 1),
+                                       (5, 9, 4, 1, 1), (8, 17, 3, 2, 1), (4, 3, 64, 1, 1), (8, 2, 70, 160, 1)])
+@pytest.mark.parametrize("sys_name", ["state", "unitary"])
+def test_edge_shapes(D, K, N, M, R, sys_name):
+    """Degenerate and ragged shapes: single slice / control / dimension 1, K > 8 (gradient reduction tail), chain
+    counts on both sides of the strategy thresholds."""
+    T = 0.7
+    members = [random_system(D, K, seed=40 + k + D, unitary_targets=(sys_name == "unitary")) for k in range(M)]
+    wts = np.linspace(0.5, 1.5, M)
+    xs = np.random.default_rng(N).uniform(-1, 1, (R, K, N))
+    with qoc.GrapeEvaluator(members, T, N, SYS[sys_name], wts=wts, n_pulses=R) as ev:
+        F, G = ev.eval(xs if R > 1 else xs[0])
+    for r in range(R):
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, xs[r], T, SYS[sys_name])
+        assert_parity(F[r] if R > 1 else F, G[r] if R > 1 else G, Fo, Go)
