@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--pulses", type=int, default=0, help="multi-start pulses per step (0 = config default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
+                    help="N > 1: fused one-shot all-reduce over NVLink peer memory (default) or torch.distributed NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -171,6 +173,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     members, wts = cfg["members"], cfg["wts"]
@@ -197,7 +200,19 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
+    oneshot = world > 1 and sharded and args.allreduce == "oneshot"
+    if oneshot:                                    # exchange the CUDA IPC handles of the per-rank exchange buffers
+        handles = [None] * world
+        dist.all_gather_object(handles, ev.comm_export())
+        ev.comm_connect(world, rank, handles)
+        parallelism += " (one-shot NVLink peer-memory all-reduce kernel)"
+    elif world > 1 and sharded:
+        parallelism += " (NCCL all-reduce)"
+
     def step_device():
+        if oneshot:
+            ev.eval_allreduce_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
+            return
         ev.eval_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
         if world > 1 and sharded:
             dist.all_reduce(fg_dev)

@@ -114,6 +114,21 @@ int qoc_total_propagator(qoc_handle* h, const double* x, double* U);
  * pw_gen_save! (:80-92) for mode 2:  out [R][M][N][D*D]. */
 int qoc_propagators(qoc_handle* h, const double* x, double* out, int mode);
 
+/* ---- multi-GPU, one process per GPU: fused one-shot all-reduce of [F|G] over NVLink peer memory -------------------
+ * Replaces the cross-shard part of the ensemble reduction `sum(gradient .* wts, dims = 1)` (src/solve.jl:171-191) when
+ * the members are sharded over GPUs.  Each rank publishes its weighted partial in a CUDA-IPC shared exchange buffer,
+ * raises an epoch flag in every peer, and sums all peers' partials in fixed rank order (deterministic, bit-identical on
+ * all ranks).  The host side only has to carry the 64-byte IPC handles between processes (e.g. torch.distributed
+ * all_gather_object, MPI, a file).
+ *   qoc_comm_export   allocate this rank's exchange buffer and return its IPC handle
+ *   qoc_comm_connect  open the peers' buffers; handles = [world][QOC_IPC_HANDLE_BYTES], own entry included
+ *   qoc_eval_allreduce_device   like qoc_eval_device, but FG_dev receives the sum over all ranks */
+#define QOC_IPC_HANDLE_BYTES 64
+#define QOC_MAX_RANKS 16
+int qoc_comm_export(qoc_handle* h, unsigned char* handle /* [QOC_IPC_HANDLE_BYTES] */);
+int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsigned char* handles);
+int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);
+
 int qoc_get_stats(qoc_handle* h, qoc_stats* out);
 /* Message of the last error on this handle (or of the last failed qoc_create when h == NULL). */
 const char* qoc_last_error(qoc_handle* h);

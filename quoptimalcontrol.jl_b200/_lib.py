@@ -10,9 +10,11 @@ STATE_TRANSFER, UNITARY_GATE, COHERENCE_TRANSFER = 0, 1, 2
 GRAD_FIRST_ORDER, GRAD_EXACT = 0, 1
 REF_INPLACE, REF_STATIC = 0, 1
 SHARED_A, SHARED_B, SHARED_XI, SHARED_XT = 1, 2, 4, 8
+IPC_HANDLE_BYTES = 64
 
 EXPORTS = ["qoc_version", "qoc_create", "qoc_destroy", "qoc_set_system", "qoc_eval", "qoc_eval_device",
-           "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error"]
+           "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error",
+           "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device"]
 
 
 class QocDesc(C.Structure):
@@ -57,6 +59,9 @@ def load():
     lib.qoc_total_propagator.argtypes = [vp, vp, vp]
     lib.qoc_propagators.argtypes = [vp, vp, vp, C.c_int]
     lib.qoc_get_stats.argtypes = [vp, C.POINTER(QocStats)]
+    lib.qoc_comm_export.argtypes = [vp, vp]
+    lib.qoc_comm_connect.argtypes = [vp, C.c_int, C.c_int, vp]
+    lib.qoc_eval_allreduce_device.argtypes = [vp, vp, vp, C.c_int, vp]
     for name in EXPORTS:
         if name not in ("qoc_version", "qoc_last_error"):
             getattr(lib, name).restype = C.c_int

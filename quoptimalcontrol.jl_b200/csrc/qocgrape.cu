@@ -43,6 +43,13 @@ struct qoc_handle {
   long long ws_bytes = 0;
   qoc_stats st{};
   BigState* big = nullptr;
+  // one-shot NVLink all-reduce (qoc_comm_*)
+  char* comm_local = nullptr;            // this rank's exchange buffer: data[2][n] doubles, then flags[2][QOC_MAX_RANKS]
+  char* comm_peer_host[QOC_MAX_RANKS] = {};
+  char** comm_peers = nullptr;           // device array of the peers' base pointers
+  int comm_world = 0, comm_rank = -1;
+  unsigned long long comm_epoch = 0;
+  size_t comm_n = 0;
 };
 
 #define QOC_CUDA(h, call)                                                                           \
@@ -217,6 +224,9 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->big) big_destroy(h->big);
+  for (int r = 0; r < h->comm_world; r++) if (r != h->comm_rank && h->comm_peer_host[r]) cudaIpcCloseMemHandle(h->comm_peer_host[r]);
+  if (h->comm_local) cudaFree(h->comm_local);
+  if (h->comm_peers) cudaFree(h->comm_peers);
   void* bufs[] = {h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
@@ -561,6 +571,88 @@ extern "C" int qoc_propagators(qoc_handle* h, const double* x, double* out, int 
   QOC_CUDA(h, cudaMemcpyAsync(out, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ one-shot all-reduce
+// Exchange buffer layout per rank: double data[2][n]; unsigned long long flags[2][QOC_MAX_RANKS].
+// Epoch e uses half b = e & 1.  A rank can only be one epoch ahead of its slowest peer (it needs that peer's flag to
+// finish an epoch), so two halves suffice: nobody overwrites a half that a peer may still be reading.
+__global__ void oneshot_allreduce_kernel(char* const* peers, int world, int rank, unsigned long long epoch, size_t n,
+                                         double* __restrict__ out) {
+  const int b = (int)(epoch & 1);
+  const size_t flags_off = 2 * n * sizeof(double);
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    // this rank's partial was written by the preceding kernel on the same stream; publish it system-wide, then signal
+    __threadfence_system();
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + flags_off) + b * QOC_MAX_RANKS + rank;
+    *f = epoch;
+  }
+  // wait for every peer's signal in OUR flag array (local memory polls)
+  const volatile unsigned long long* mine = reinterpret_cast<const volatile unsigned long long*>(peers[rank] + flags_off) + b * QOC_MAX_RANKS;
+  if (threadIdx.x < world) { while (mine[threadIdx.x] < epoch) __nanosleep(64); }
+  __syncthreads();
+  __threadfence_system();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < world; r++) {
+      const volatile double* src = reinterpret_cast<const volatile double*>(peers[r]) + (size_t)b * n;
+      s += src[i];                                   // fixed rank order: bit-identical on every rank
+    }
+    out[i] = s;
+  }
+}
+
+extern "C" int qoc_comm_export(qoc_handle* h, unsigned char* handle) {
+  if (!h || !handle) return QOC_EINVAL;
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  if (!h->comm_local) {
+    h->comm_n = (size_t)h->d.R * (h->NK + 1);
+    const size_t bytes = 2 * h->comm_n * sizeof(double) + 2 * QOC_MAX_RANKS * sizeof(unsigned long long);
+    QOC_CUDA(h, cudaMalloc((void**)&h->comm_local, bytes));
+    QOC_CUDA(h, cudaMemset(h->comm_local, 0, bytes));
+    QOC_CUDA(h, cudaDeviceSynchronize());
+    h->ws_bytes += (long long)bytes;
+  }
+  cudaIpcMemHandle_t ih;
+  QOC_CUDA(h, cudaIpcGetMemHandle(&ih, h->comm_local));
+  static_assert(sizeof(cudaIpcMemHandle_t) == QOC_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle, &ih, QOC_IPC_HANDLE_BYTES);
+  return QOC_OK;
+}
+
+extern "C" int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsigned char* handles) {
+  if (!h || !handles || world < 1 || world > QOC_MAX_RANKS || rank < 0 || rank >= world) { if (h) h->err = "qoc_comm_connect: bad argument"; return QOC_EINVAL; }
+  if (!h->comm_local) { h->err = "qoc_comm_connect: call qoc_comm_export first"; return QOC_EINVAL; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { h->comm_peer_host[r] = h->comm_local; continue; }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handles + (size_t)r * QOC_IPC_HANDLE_BYTES, QOC_IPC_HANDLE_BYTES);
+    void* ptr = nullptr;
+    QOC_CUDA(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->comm_peer_host[r] = (char*)ptr;
+  }
+  if (!h->comm_peers) QOC_CUDA(h, cudaMalloc((void**)&h->comm_peers, QOC_MAX_RANKS * sizeof(char*)));
+  QOC_CUDA(h, cudaMemcpy(h->comm_peers, h->comm_peer_host, QOC_MAX_RANKS * sizeof(char*), cudaMemcpyHostToDevice));
+  h->comm_world = world; h->comm_rank = rank; h->comm_epoch = 0;
+  return QOC_OK;
+}
+
+extern "C" int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream) {
+  if (!h) return QOC_EINVAL;
+  if (!x_dev || !FG_dev) { h->err = "qoc_eval_allreduce_device: null pointer"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_eval_allreduce_device: qoc_set_system has not been called"; return QOC_EINVAL; }
+  if (h->comm_world < 1) { h->err = "qoc_eval_allreduce_device: qoc_comm_connect has not been called"; return QOC_EINVAL; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long epoch = ++h->comm_epoch;
+  double* mine = reinterpret_cast<double*>(h->comm_local) + (size_t)(epoch & 1) * h->comm_n;
+  if (!want_gradient) QOC_CUDA(h, cudaMemsetAsync(mine, 0, h->comm_n * sizeof(double), st));   // G part undefined otherwise
+  int rc = eval_device_on(h, x_dev, mine, want_gradient, st);
+  if (rc != QOC_OK) return rc;
+  const int blocks = (int)std::min<size_t>((h->comm_n + 255) / 256, 64);
+  oneshot_allreduce_kernel<<<blocks, 256, 0, st>>>(h->comm_peers, h->comm_world, h->comm_rank, epoch, h->comm_n, FG_dev);
+  return launch_check(h, "oneshot_allreduce_kernel");
 }
 
 extern "C" int qoc_get_stats(qoc_handle* h, qoc_stats* out) {

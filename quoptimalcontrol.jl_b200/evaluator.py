@@ -81,6 +81,24 @@ class GrapeEvaluator:
         """Asynchronous evaluation on device pointers (ints): x [R][N][K], FG [R][1 + N*K]."""
         self._check(self._lib.qoc_eval_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
 
+    # ---- multi-GPU: one-shot all-reduce over NVLink peer memory (one process per GPU) ----
+    def comm_export(self) -> bytes:
+        """Allocate the exchange buffer; returns its 64-byte CUDA IPC handle (to be all-gathered by the caller)."""
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        self._check(self._lib.qoc_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_connect(self, world, rank, handles):
+        """handles: list of `world` IPC handles (bytes) in rank order, own entry included."""
+        blob = b"".join(handles)
+        if len(blob) != world * _lib.IPC_HANDLE_BYTES:
+            raise ValueError("expected one 64-byte handle per rank")
+        self._check(self._lib.qoc_comm_connect(self._h, int(world), int(rank), blob))
+
+    def eval_allreduce_device(self, x_dev_ptr, fg_dev_ptr, want_grad=True, stream=None):
+        """qoc_eval_device + fused one-shot all-reduce: FG receives the sum over all ranks (async on `stream`)."""
+        self._check(self._lib.qoc_eval_allreduce_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
+
     def total_propagator(self, x):
         """pw_evolve with U0 = I (src/timeevolution.jl:28-39): U[R, M, D, D] (squeezed for R = M = 1)."""
         xb = self._pack_x(x)

@@ -1,0 +1,67 @@
+"""Two-GPU test of the sharded ensemble with the fused one-shot NVLink all-reduce (qoc_comm_* / qoc_eval_allreduce_device).
+Skipped on single-GPU boxes; run with `gpurun --gpus 2`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import quoptimalcontrol_jl_b200 as qoc
+    from oracle import grape_oracle as orc
+    from conftest import random_system
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)   # only carries handles
+    M, K, N, T, D = 7, 3, 40, 1.0, 8
+    members = [random_system(D, K, seed=80 + k, unitary_targets=True) for k in range(M)]
+    wts = np.linspace(0.05, 0.25, M)
+    lo, hi = qoc.shard_bounds(M, rank, world)
+    ev = qoc.GrapeEvaluator(members[lo:hi], T, N, orc.UNITARY_GATE, wts=wts[lo:hi], device=rank)
+    handles = [None] * world
+    dist.all_gather_object(handles, ev.comm_export())
+    ev.comm_connect(world, rank, handles)
+    dev = torch.device("cuda", rank)
+    errs = []
+    for it in range(5):                                   # several epochs: exercises both halves of the exchange buffer
+        x = np.random.default_rng(it).uniform(-1, 1, (K, N))
+        x_dev = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
+        fg = torch.zeros(N * K + 1, dtype=torch.float64, device=dev)
+        ev.eval_allreduce_device(x_dev.data_ptr(), fg.data_ptr(), True, None)
+        torch.cuda.synchronize()
+        out = fg.cpu().numpy()
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, x, T, orc.UNITARY_GATE)
+        G = out[1:].reshape(N, K).T
+        errs.append((abs(out[0] - Fo), float(np.max(np.abs(G - Go)) / np.max(np.abs(Go)))))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, out.tobytes())
+        assert all(g == gathered[0] for g in gathered), "ranks disagree bitwise"
+    q.put((rank, errs))
+    ev.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_oneshot_allreduce_two_gpus():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        for ef, eg in errs:
+            assert ef < 1e-10 and eg < 1e-8
