@@ -202,10 +202,20 @@ def main():
 
     oneshot = world > 1 and sharded and args.allreduce == "oneshot"
     if oneshot:                                    # exchange the CUDA IPC handles of the per-rank exchange buffers
-        handles = [None] * world
-        dist.all_gather_object(handles, ev.comm_export())
-        ev.comm_connect(world, rank, handles)
-        parallelism += " (one-shot NVLink peer-memory all-reduce kernel)"
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ev.comm_export())
+            ev.comm_connect(world, rank, handles)
+            ok = 1
+        except Exception as exc:                   # e.g. CUDA IPC not permitted on this box
+            ok, why = 0, str(exc)
+        t = torch.tensor([ok], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)   # all ranks must agree on the collective they use
+        if int(t.item()) == 1:
+            parallelism += " (one-shot NVLink peer-memory all-reduce kernel)"
+        else:
+            oneshot = False
+            parallelism += " (NCCL all-reduce; one-shot unavailable)"
     elif world > 1 and sharded:
         parallelism += " (NCCL all-reduce)"
 
