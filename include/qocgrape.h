@@ -14,7 +14,8 @@
  *   - every function returns a status (0 = QOC_OK); no exception crosses the boundary;
  *   - the library copies inputs during the call and never retains host pointers;
  *   - a handle is used by one thread at a time; different handles are independent;
- *   - there is NO CPU fallback: without a CUDA device or for unsupported shapes an error is returned.
+ *   - there is NO CPU fallback: without a CUDA device or for unsupported shapes an error is returned;
+ *   - for D > 16 qoc_eval_device synchronises its stream once per evaluation (a 4-byte read of the scaling power).
  */
 #ifndef QOCGRAPE_H
 #define QOCGRAPE_H

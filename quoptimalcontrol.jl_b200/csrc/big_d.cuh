@@ -9,7 +9,8 @@
 //            -- evolve_func!, /root/reference/src/GRAPE.jl:53-75, 216-251
 //   phase 5  W_t = S_t C_t' (- C_t' S_t for density types) for all slices, then K trace-dots per slice over the
 //            non-zeros of B_c  -- grad_func!, /root/reference/src/GRAPE.jl:261-287;  fom_func, cost_functions.jl:99-111
-// First-order gradient only (the exact mode of this path is not implemented: QOC_EUNSUPPORTED).
+// Exact gradient (GRAD_EXACT): phases 1-4 as above, then per slice the direction matrix Y_t, the Frechet derivative
+// L(G_t, Y_t) of the Taylor-8 scheme (8 batched GEMM launches + 2 per squaring) and the same trace-dots.
 #pragma once
 #include <string>
 #include <vector>
@@ -91,13 +92,16 @@ __global__ void big_fom_kernel(const double2* __restrict__ X, const double2* __r
 //   f = i*dt (density) or 2*(+-i dt)*tau (unitary, tau read from tau_fom)
 struct BigTraceParams {
   const double2* W; int D, K, N; const int* coo_ptr; const int2* coo_idx; const double2* coo_val;
-  const double* tau_fom; int unitary; double dt; int sign_static; double* g /* [N][K] */;
+  const double* tau_fom; int unitary; double dt; int sign_static; double* g /* [N][K] */; int exact; double invD2;
 };
 __global__ void big_trace_kernel(const BigTraceParams p) {
   __shared__ double sr[128];
   int t = blockIdx.x, c = blockIdx.y;
   double fr, fi;
-  if (p.unitary) { double sg = 2.0 * p.sign_static * p.dt; fr = -sg * p.tau_fom[1]; fi = sg * p.tau_fom[0]; }
+  if (p.exact) {   // -(2/D^2) (conj(tau)) (-i dt): tau is already folded into Y for the density types
+    const double k = 2.0 * p.dt * p.invD2;
+    if (p.unitary) { fr = k * p.tau_fom[1]; fi = k * p.tau_fom[0]; } else { fr = 0.0; fi = k; }
+  } else if (p.unitary) { double sg = 2.0 * p.sign_static * p.dt; fr = -sg * p.tau_fom[1]; fi = sg * p.tau_fom[0]; }
   else { fr = 0.0; fi = p.dt; }
   const double2* W = p.W + (size_t)t * p.D * p.D;
   double acc = 0;
@@ -133,6 +137,10 @@ struct BigState {
   cudaEvent_t evFork = nullptr, evA = nullptr, evB = nullptr;
   double2 *A = nullptr, *B = nullptr, *Xi = nullptr, *Xt = nullptr;   // [M] padded systems
   double2* buf[7] = {};                                               // (N+1) matrices each
+  double2* xbuf[11] = {};                                             // exact gradient only: S, C, Y, T1, T2, dG2, dY1, dL8, dR8, dP, dPb
+  int exact = 0, s_last = 0;
+  double2* Pfinal = nullptr;
+  std::vector<double2*> pchain;                                       // exact gradient: P_1, P_2, ... (intermediate squares), grown on demand
   double2 *Q = nullptr, *T = nullptr, *tmpF = nullptr, *tmpB = nullptr;   // 2*Cn, Cn, Cn, Cn matrices
   int *tab2A = nullptr, *tab2T = nullptr, *tab0 = nullptr, *tab4F = nullptr, *tab4B = nullptr, *s_dev = nullptr;
   float* norms = nullptr;
@@ -161,6 +169,8 @@ static inline void big_destroy(BigState* s) {
                   s->s_dev, s->norms, s->tau_fom, s->gk, s->coo_ptr, s->coo_idx, s->coo_val};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& b : s->buf) if (b) cudaFree(b);
+  for (auto& b : s->xbuf) if (b) cudaFree(b);
+  for (auto& b : s->pchain) if (b) cudaFree(b);
   if (s->sA) cudaStreamDestroy(s->sA);
   if (s->sB) cudaStreamDestroy(s->sB);
   if (s->evFork) cudaEventDestroy(s->evFork);
@@ -170,10 +180,10 @@ static inline void big_destroy(BigState* s) {
 }
 
 static inline int big_create(BigState** out, const qoc_desc& d, std::string& err, long long& ws_total) {
-  if (d.gradient == QOC_GRAD_EXACT) { err = "exact gradient is not implemented for D > 16"; return QOC_EUNSUPPORTED; }
   BigState* s = new BigState();
   *out = s;
   s->d = d;
+  s->exact = d.gradient == QOC_GRAD_EXACT;
   s->Dp = ((d.D + 63) / 64) * 64;
   s->DD = (size_t)s->Dp * s->Dp;
   s->unitary = d.sys_type == QOC_UNITARY_GATE;
@@ -198,6 +208,7 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
   if ((rc = big_alloc(s, &s->Xi, (size_t)d.M * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->Xt, (size_t)d.M * DD, err))) return rc;
   for (auto& b : s->buf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
+  if (s->exact) for (auto& b : s->xbuf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->Q, (size_t)2 * Cn * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->T, (size_t)Cn * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->tmpF, (size_t)Cn * DD, err))) return rc;
@@ -280,8 +291,8 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
 
 // ---------------------------------------------------------------------------------------------- launches
 static inline BatchedMat bmat(const double2* p, long stride, const int* table = nullptr, int offset = 0) { return BatchedMat{p, stride, table, offset}; }
-static inline EpiOut eout(BatchedMat m, double alpha = 1.0, int apow = 0, double ident = 0.0) { EpiOut e{}; e.m = m; e.alpha = alpha; e.alpha_pow2 = apow; e.ident = ident; e.naux = 0; return e; }
-static inline void eaux(EpiOut& e, BatchedMat m, double coef, int pow2 = 0) { e.aux[e.naux].m = m; e.aux[e.naux].coef = coef; e.aux[e.naux].pow2 = pow2; e.naux++; }
+static inline EpiOut eout(BatchedMat m, double alpha = 1.0, int apow = 0, double ident = 0.0, int acz = 0) { EpiOut e{}; e.m = m; e.alpha = alpha; e.alpha_pow2 = apow; e.alpha_cz = acz; e.ident = ident; e.naux = 0; return e; }
+static inline void eaux(EpiOut& e, BatchedMat m, double coef, int pow2 = 0, int cz = 0) { e.aux[e.naux].m = m; e.aux[e.naux].coef = coef; e.aux[e.naux].pow2 = pow2; e.aux[e.naux].cz = cz; e.naux++; }
 
 static int big_gemm(BigState* s, int opA, int opB, GemmParams& p, cudaStream_t st, std::string& err, qoc_stats& stats) {
   typedef void (*kfn)(const GemmParams);
@@ -334,6 +345,24 @@ static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaSt
   int s_host = 0;
   BIG_CUDA(cudaMemcpyAsync(&s_host, s->s_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   BIG_CUDA(cudaStreamSynchronize(st));
+  s->s_last = s_host;
+  if (s->exact) {   // keep every intermediate square for the Frechet chain rule: P_0 = buf[5], P_1 = xbuf[11], P_2 = xbuf[12]
+    if (s_host > 12) { err = "exact gradient for D > 16 supports at most 12 squarings (||dt*H||_1 <= 284): use more slices"; return QOC_EUNSUPPORTED; }
+    while ((int)s->pchain.size() < s_host) {      // intermediate squares are needed by the chain rule; allocated on first use
+      double2* nb = nullptr;
+      if ((rc = big_alloc(s, &nb, (size_t)(N + 1) * DD, err))) return rc;
+      s->pchain.push_back(nb);
+    }
+    std::vector<double2*> chain(1, s->buf[5]);
+    chain.insert(chain.end(), s->pchain.begin(), s->pchain.end());
+    for (int j = 0; j < s_host; j++) {
+      GemmParams q{};
+      q.batch = N; q.A = bmat(chain[j], sd); q.B = bmat(chain[j], sd); q.nout = 1; q.out[0] = eout(bmat(chain[j + 1], sd));
+      if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+    }
+    s->Pfinal = chain[s_host];
+    return QOC_OK;
+  }
   for (int j = 0; j < s_host; j++) {
     GemmParams q{};
     q.batch = N; q.A = bmat(P, sd); q.B = bmat(P, sd); q.nout = 1; q.out[0] = eout(bmat(P2, sd));
@@ -341,13 +370,14 @@ static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaSt
     std::swap(P, P2);
   }
   if (P != s->buf[5]) std::swap(s->buf[5], s->buf[6]);   // keep "buf[5] is P"
+  s->Pfinal = s->buf[5];
   return QOC_OK;
 }
 
 // phase 2: chunk totals T_c (batch Cn, Lmax-1 lock steps)
 static int big_chunk_totals(BigState* s, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const long sd = (long)s->DD; const int Cn = s->Cn;
-  double2* P = s->buf[5];
+  double2* P = s->Pfinal;
   int rc;
   for (int c = 0; c < Cn; c++)
     if (s->len[c] == 1) BIG_CUDA(cudaMemcpyAsync(s->T + (size_t)c * s->DD, P + (size_t)s->start[c] * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
@@ -370,7 +400,7 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
   const int N = d.N, Cn = s->Cn, U = s->unitary;
   int rc;
   if ((rc = big_propagators_phase(s, k, x_dev, st, err, stats))) return rc;
-  double2 *P = s->buf[5], *S = s->buf[1], *C = s->buf[2], *W = s->buf[3];
+  double2 *P = s->Pfinal, *S = s->exact ? s->xbuf[0] : s->buf[1], *C = s->exact ? s->xbuf[1] : s->buf[2], *W = s->buf[3];
   if ((rc = big_chunk_totals(s, st, err, stats))) return rc;
   // ---- phase 3: boundary states (stream sA) and boundary costates (stream sB), short sequential chains ----
   BIG_CUDA(cudaMemcpyAsync(S, s->Xi + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
@@ -429,10 +459,65 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
   BIG_CUDA(cudaStreamWaitEvent(st, s->evB, 0));
   // ---- figure of merit from S[N] and Xt ----
   const double invD2 = 1.0 / ((double)d.D * d.D);
-  if (U) big_fom_kernel<<<1, 256, 0, st>>>(S + (size_t)N * DD, s->Xt + (size_t)k * DD, (int)DD, 1, invD2, s->tau_fom);
+  if (U && !s->exact) big_fom_kernel<<<1, 256, 0, st>>>(S + (size_t)N * DD, s->Xt + (size_t)k * DD, (int)DD, 1, invD2, s->tau_fom);
   else big_fom_kernel<<<1, 256, 0, st>>>(s->Xt + (size_t)k * DD, S + (size_t)N * DD, (int)DD, 0, invD2, s->tau_fom);
   BIG_COUNT();
   if (!want_grad) return QOC_OK;
+  if (s->exact) {
+    // ---- exact gradient: Y_t, Frechet derivative Lam_t = L(G_t, Y_t), trace-dots over Lam_t ----
+    double2 *G = s->buf[0], *G2 = s->buf[1], *Y1 = s->buf[2], *L8 = s->buf[3], *R8 = s->buf[4];
+    double2 *Y = s->xbuf[2], *T1 = s->xbuf[3], *T2 = s->xbuf[4], *dG2 = s->xbuf[5], *dY1 = s->xbuf[6], *dL8 = s->xbuf[7],
+            *dR8 = s->xbuf[8], *dP = s->xbuf[9], *dPb = s->xbuf[10];
+    const double2* C1 = C + DD;                      // costate after slice t
+    GemmParams p{}; p.batch = N; p.s_ptr = s->s_dev; p.cz_ptr = s->tau_fom;
+    auto run = [&](int opA, int opB) { return big_gemm(s, opA, opB, p, st, err, stats); };
+    if (U) {
+      p.A = bmat(S, sd); p.B = bmat(C1, sd); p.nout = 1; p.out[0] = eout(bmat(Y, sd));                        // Y = S_t C_{t+1}'
+      if ((rc = run(0, 1))) return rc;
+    } else {
+      p.A = bmat(P, sd); p.B = bmat(C1, sd); p.nout = 1; p.out[0] = eout(bmat(T1, sd)); if ((rc = run(1, 1))) return rc;   // P' C'
+      p.out[0] = eout(bmat(T2, sd)); if ((rc = run(1, 0))) return rc;                                                      // P' C
+      p.A = bmat(S, sd); p.B = bmat(T1, sd); p.out[0] = eout(bmat(Y, sd)); if ((rc = run(0, 0))) return rc;                // S P' C'
+      p.A = bmat(S, sd); p.B = bmat(T2, sd);
+      p.out[0] = eout(bmat(Y, sd), 1.0, 0, 0.0, 1); eaux(p.out[0], bmat(Y, sd), 1.0, 0, 2);                               // tau S' P' C + conj(tau) Y
+      if ((rc = run(1, 0))) return rc;
+    }
+    // dG2 = (Y G + G Y)/4^s ; dY1 = x1 Y/2^s + x2 dG2
+    p.A = bmat(Y, sd); p.B = bmat(G, sd); p.nout = 1; p.out[0] = eout(bmat(dG2, sd), 1.0, 2); if ((rc = run(0, 0))) return rc;
+    p.A = bmat(G, sd); p.B = bmat(Y, sd); p.nout = 2;
+    p.out[0] = eout(bmat(dY1, sd), BT8_X2, 2); eaux(p.out[0], bmat(dG2, sd), BT8_X2); eaux(p.out[0], bmat(Y, sd), BT8_X1, 1);
+    p.out[1] = eout(bmat(dG2, sd), 1.0, 2); eaux(p.out[1], bmat(dG2, sd), 1.0);
+    if ((rc = run(0, 0))) return rc;
+    // dG4 = dG2 Y1 + G2 dY1 ; dR8 = x5 Y/2^s + x6 dG2 + x7 dG4 ; dL8 = x3 dG2 + dG4
+    p.A = bmat(dG2, sd); p.B = bmat(Y1, sd); p.nout = 1; p.out[0] = eout(bmat(dL8, sd)); if ((rc = run(0, 0))) return rc;
+    p.A = bmat(G2, sd); p.B = bmat(dY1, sd); p.nout = 2;
+    p.out[0] = eout(bmat(dR8, sd), BT8_X7); eaux(p.out[0], bmat(dL8, sd), BT8_X7); eaux(p.out[0], bmat(Y, sd), BT8_X5, 1); eaux(p.out[0], bmat(dG2, sd), BT8_X6);
+    p.out[1] = eout(bmat(dL8, sd), 1.0); eaux(p.out[1], bmat(dL8, sd), 1.0); eaux(p.out[1], bmat(dG2, sd), BT8_X3);
+    if ((rc = run(0, 0))) return rc;
+    // dP = dL8 R8 + L8 dR8 + Y/2^s + y2 dG2
+    p.A = bmat(dL8, sd); p.B = bmat(R8, sd); p.nout = 1;
+    p.out[0] = eout(bmat(dP, sd), 1.0); eaux(p.out[0], bmat(Y, sd), 1.0, 1); eaux(p.out[0], bmat(dG2, sd), BT8_Y2);
+    if ((rc = run(0, 0))) return rc;
+    p.A = bmat(L8, sd); p.B = bmat(dR8, sd); p.out[0] = eout(bmat(dP, sd), 1.0); eaux(p.out[0], bmat(dP, sd), 1.0);
+    if ((rc = run(0, 0))) return rc;
+    // squarings: dP <- dP P_j + P_j dP
+    std::vector<double2*> chain(1, s->buf[5]);
+    chain.insert(chain.end(), s->pchain.begin(), s->pchain.end());
+    for (int j = 0; j < s->s_last; j++) {
+      p.A = bmat(dP, sd); p.B = bmat(chain[j], sd); p.out[0] = eout(bmat(dPb, sd)); if ((rc = run(0, 0))) return rc;
+      p.A = bmat(chain[j], sd); p.B = bmat(dP, sd); p.out[0] = eout(bmat(dPb, sd), 1.0); eaux(p.out[0], bmat(dPb, sd), 1.0);
+      if ((rc = run(0, 0))) return rc;
+      std::swap(dP, dPb);
+    }
+    if (d.K > 0) {
+      BigTraceParams tp;
+      tp.W = dP; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
+      tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = 1; tp.g = s->gk; tp.exact = 1; tp.invD2 = invD2;
+      big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
+      BIG_COUNT();
+    }
+    return QOC_OK;
+  }
   // ---- phase 5: W_t for all slices, then trace-dots ----
   {
     GemmParams p{}; p.batch = N; p.nout = 1;
@@ -446,7 +531,7 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
   if (d.K > 0) {
     BigTraceParams tp;
     tp.W = W; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
-    tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.g = s->gk;
+    tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.g = s->gk; tp.exact = 0; tp.invD2 = 0.0;
     big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
     BIG_COUNT();
   }
@@ -484,7 +569,7 @@ static inline int big_propagators(BigState* s, const double* x_dev, double2* out
   for (int r = 0; r < d.R; r++)
     for (int k = 0; k < d.M; k++) {
       const double2* src;
-      if (mode == 0) { if ((rc = big_propagators_phase(s, k, x_dev + (size_t)r * NK, st, err, stats))) return rc; src = s->buf[5]; }
+      if (mode == 0) { if ((rc = big_propagators_phase(s, k, x_dev + (size_t)r * NK, st, err, stats))) return rc; src = s->Pfinal; }
       else {
         dim3 ga((unsigned)((s->DD + 255) / 256), (d.N + 63) / 64);
         big_assemble_kernel<<<ga, 256, 0, st>>>(s->A + (size_t)k * s->DD, s->B + (size_t)k * std::max(d.K, 1) * s->DD, x_dev + (size_t)r * NK,

@@ -27,10 +27,11 @@ struct BatchedMat {
   const int* table;
   int offset;
 };
-struct EpiAux { BatchedMat m; double coef; int pow2; };   // contributes coef * 2^(-s*pow2) * M
+// cz: 0 = real coefficient; 1 = additionally multiplied by the complex device scalar *cz_ptr; 2 = by its conjugate
+struct EpiAux { BatchedMat m; double coef; int pow2; int cz; };   // contributes coef * 2^(-s*pow2) * [cz] * M
 struct EpiOut {
   BatchedMat m;         // destination (ptr is written through a const_cast)
-  double alpha; int alpha_pow2;   // alpha * 2^(-s*alpha_pow2) * acc
+  double alpha; int alpha_pow2; int alpha_cz;   // alpha * 2^(-s*alpha_pow2) * [cz] * acc
   double ident; int naux;
   EpiAux aux[3];
 };
@@ -40,6 +41,7 @@ struct GemmParams {
   EpiOut out[2];
   int nout;
   const int* s_ptr;     // device scalar: scaling power of the exponential (may be null -> 0)
+  const double* cz_ptr; // device complex scalar (re, im) for the cz coefficient modes (may be null)
   const int* skip_ge;   // optional device scalar: if non-null and *skip_ge <= skip_level the launch is a no-op
   int skip_level;
 };
@@ -150,12 +152,18 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
     bool idl = false;
     double2* Cg = const_cast<double2*>(bm_ptr(eo.m, b, idl));
     if (idl) continue;
-    const double alpha = eo.alpha * scalbn(1.0, -s * eo.alpha_pow2);
-    const double2* auxp[3]; double auxc[3];
+    const double czr = p.cz_ptr ? p.cz_ptr[0] : 1.0, czi = p.cz_ptr ? p.cz_ptr[1] : 0.0;
+    auto ccoef = [&](double c, int pw, int mode, double& cr, double& ci) {
+      const double v = c * scalbn(1.0, -s * pw);
+      cr = mode ? v * czr : v; ci = mode == 1 ? v * czi : (mode == 2 ? -v * czi : 0.0);
+    };
+    double ar, ai;
+    ccoef(eo.alpha, eo.alpha_pow2, eo.alpha_cz, ar, ai);
+    const double2* auxp[3]; double auxr[3], auxi[3];
     for (int x = 0; x < eo.naux; x++) {
       bool dummy = false;
       auxp[x] = bm_ptr(eo.aux[x].m, b, dummy);
-      auxc[x] = eo.aux[x].coef * scalbn(1.0, -s * eo.aux[x].pow2);
+      ccoef(eo.aux[x].coef, eo.aux[x].pow2, eo.aux[x].cz, auxr[x], auxi[x]);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -165,8 +173,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
         for (int e = 0; e < 2; e++) {
           const int row = m0 + wm0 + 8 * i + g, col = n0 + wn0 + 8 * j + 2 * q + e;
           const size_t off = (size_t)col * D + row;
-          double re = alpha * acc[i][j][e], im = alpha * acc[i][j][2 + e];
-          for (int x = 0; x < eo.naux; x++) { double2 v = auxp[x][off]; re = fma(auxc[x], v.x, re); im = fma(auxc[x], v.y, im); }
+          double re = ar * acc[i][j][e] - ai * acc[i][j][2 + e], im = ar * acc[i][j][2 + e] + ai * acc[i][j][e];
+          for (int x = 0; x < eo.naux; x++) {
+            double2 v = auxp[x][off];
+            re = fma(auxr[x], v.x, fma(-auxi[x], v.y, re)); im = fma(auxr[x], v.y, fma(auxi[x], v.x, im));
+          }
           if (row == col) re += eo.ident;
           Cg[off] = make_double2(re, im);
         }

@@ -71,8 +71,36 @@ def test_propagators_and_total_big():
     assert np.max(np.abs(qoc.pw_evolve(A, B, x, K, dt, N, I) - orc.pw_evolve(A, B, x, dt, I))) < 1e-12
 
 
-def test_exact_unsupported_is_loud():
-    A, B, Xi, Xt = random_system(64, 1, seed=1)
-    with pytest.raises(qoc.QocError) as e:
-        qoc.GrapeEvaluator([(A, B, Xi, Xt)], 1.0, 4, orc.STATE_TRANSFER, gradient="exact")
+@pytest.mark.parametrize("D,N", [(64, 6), (40, 4)])
+@pytest.mark.parametrize("sys_name", ["state", "unitary", "coherence"])
+def test_exact_gradient_big(D, N, sys_name):
+    """Exact (ADGRAPE-semantics) gradient on the tiled-GEMM path: Frechet derivative of the Taylor-8 scheme."""
+    K, T = 2, 0.6
+    A, B, Xi, Xt = random_system(D, K, seed=800 + D, hermitian=(sys_name != "coherence"),
+                                 unitary_targets=(sys_name == "unitary"))
+    x = np.random.default_rng(D + 1).uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, SYS[sys_name], gradient="exact") as ev:
+        F, G = ev.eval(x)
+        F0, _ = ev.eval(x, want_grad=False)
+    Fo, Go = orc.exact_fom_and_gradient(A, B, x, T, Xi, Xt, SYS[sys_name])
+    assert_parity(F, G, Fo, Go)
+    assert_parity(F0, None, Fo, None)
+
+
+@pytest.mark.parametrize("scale", [1.5, 3.0])
+def test_exact_gradient_big_with_squarings(scale):
+    D, K, N, T = 64, 2, 3, 1.0
+    A, B, Xi, Xt = random_system(D, K, seed=12, scale=scale)
+    x = np.random.default_rng(4).uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER, gradient="exact") as ev:
+        F, G = ev.eval(x)
+    Fo, Go = orc.exact_fom_and_gradient(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert_parity(F, G, Fo, Go, ftol=1e-9, gtol=1e-7)
+
+
+def test_exact_too_many_squarings_is_loud():
+    A, B, Xi, Xt = random_system(64, 1, seed=1, scale=4000.0)
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], 1.0, 2, orc.STATE_TRANSFER, gradient="exact") as ev:
+        with pytest.raises(qoc.QocError) as e:
+            ev.eval(np.ones((1, 2)))
     assert e.value.status == qoc._lib.QOC_EUNSUPPORTED
