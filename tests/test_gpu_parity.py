@@ -219,3 +219,15 @@ def test_edge_shapes(D, K, N, M, R, sys_name):
     for r in range(R):
         Fo, Go = orc.ensemble_fom_and_gradient(members, wts, xs[r], T, SYS[sys_name])
         assert_parity(F[r] if R > 1 else F, G[r] if R > 1 else G, Fo, Go)
+
+
+@pytest.mark.parametrize("D", [4, 8, 64])
+def test_no_controls(D):
+    """K = 0: drift-only evolution, figure of merit only (empty gradient)."""
+    A, _, Xi, Xt = random_system(D, 1, seed=3)
+    N, T = 5, 0.9
+    x = np.zeros((0, N))
+    with qoc.GrapeEvaluator([(A, [], Xi, Xt)], T, N, orc.STATE_TRANSFER) as ev:
+        F, G = ev.eval(x)
+    Fo, Go = orc.fom_and_gradient_grape(A, [], x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert abs(F - Fo) < 1e-12 and G.shape == (0, N)
