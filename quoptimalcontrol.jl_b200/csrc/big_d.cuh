@@ -139,6 +139,7 @@ struct BigState {
   double2* buf[7] = {};                                               // (N+1) matrices each
   double2* xbuf[11] = {};                                             // exact gradient only: S, C, Y, T1, T2, dG2, dY1, dL8, dR8, dP, dPb
   int exact = 0, s_last = 0;
+  int herm = 0;      // drift and every control Hermitian (exact host check): propagators unitary, conjugation recursion usable
   double2* Pfinal = nullptr;
   std::vector<double2*> pchain;                                       // exact gradient: P_1, P_2, ... (intermediate squares), grown on demand
   double2 *Q = nullptr, *T = nullptr, *tmpF = nullptr, *tmpB = nullptr;   // 2*Cn, Cn, Cn, Cn matrices
@@ -262,6 +263,22 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
   if (K > 0 && (rc = rep(s->B, B, K, shared & QOC_SHARED_B))) return rc;
   if ((rc = rep(s->Xi, Xi, 1, shared & QOC_SHARED_XI))) return rc;
   if ((rc = rep(s->Xt, Xt, 1, shared & QOC_SHARED_XT))) return rc;
+  {  // Hermitian drift and controls => unitary propagators (exact elementwise test, like Julia's ishermitian)
+    auto is_herm = [&](const double* Mx) {
+      for (int c = 0; c < D; c++)
+        for (int r = 0; r <= c; r++) {
+          const double* a = Mx + 2 * ((size_t)c * D + r); const double* b = Mx + 2 * ((size_t)r * D + c);
+          if (a[0] != b[0] || a[1] != -b[1]) return false;
+        }
+      return true;
+    };
+    bool h = true;
+    const int nA = (shared & QOC_SHARED_A) ? 1 : M, nB = (shared & QOC_SHARED_B) ? 1 : M;
+    for (int k = 0; k < nA && h; k++) h = is_herm(A + 2 * (size_t)k * dd);
+    for (int k = 0; k < nB * K && h; k++) h = is_herm(B + 2 * (size_t)k * dd);
+    s->herm = h ? 1 : 0;
+    if (const char* e = getenv("QOC_BIG_HERM")) s->herm = s->herm && atoi(e) != 0;   // tuning / A-B testing override
+  }
   // COO lists of the non-zeros of every control (indices in the padded matrix): tr(B W) = sum_nz B[a][b] W[b][a]
   std::vector<int> ptr; std::vector<int2> idx; std::vector<double2> val;
   s->coo_member_off.assign(M, 0);
@@ -394,6 +411,73 @@ static int big_chunk_totals(BigState* s, cudaStream_t st, std::string& err, qoc_
   return QOC_OK;
 }
 
+// Closed systems (Hermitian drift and controls): every P_t is unitary, hence V_t = U_N U_t' and
+//   W_t = S_t C_t' (- C_t' S_t) = U_t W_0 U_t',   W_0 = Xi C_0' (- C_0' Xi),   C_0 = U_N' Xt (U_N).
+// One forward conjugation recursion W_{t+1} = P_t W_t P_t' replaces the separate state and costate sweeps and the
+// per-slice W products: 7 GEMMs per slice instead of 11.  Same figure of merit and gradient to rounding.
+static int big_eval_member_unitary(BigState* s, int k, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const qoc_desc& d = s->d;
+  const size_t DD = s->DD; const long sd = (long)DD;
+  const int N = d.N, Cn = s->Cn, U = s->unitary;
+  int rc;
+  double2 *P = s->Pfinal, *W = s->buf[3];
+  const double2* Xi = s->Xi + (size_t)k * DD;
+  const double2* Xt = s->Xt + (size_t)k * DD;
+  GemmParams p{}; p.batch = 1; p.nout = 1;
+  // U_N = T_{Cn-1} ... T_0
+  const double2* Un = s->T;
+  for (int c = 1; c < Cn; c++) {
+    double2* dst = s->Q + (size_t)(c & 1) * Cn * DD;
+    p.A = bmat(s->T + (size_t)c * DD, 0); p.B = bmat(Un, 0); p.out[0] = eout(bmat(dst, 0));
+    if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+    Un = dst;
+  }
+  // C_0 = U_N' Xt (U_N)
+  double2* C0 = s->tmpB;
+  if (U) { p.A = bmat(Un, 0); p.B = bmat(Xt, 0); p.out[0] = eout(bmat(C0, 0)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc; }
+  else {
+    p.A = bmat(Xt, 0); p.B = bmat(Un, 0); p.out[0] = eout(bmat(s->tmpF, 0)); if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+    p.A = bmat(Un, 0); p.B = bmat(s->tmpF, 0); p.out[0] = eout(bmat(C0, 0)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
+  }
+  // figure of merit: unitary tau = tr(S_N' Xt) = tr(Xi' C_0); density tau = tr(Xt' S_N) = tr(C_0' Xi)
+  const double invD2 = 1.0 / ((double)d.D * d.D);
+  if (U) big_fom_kernel<<<1, 256, 0, st>>>(Xi, C0, (int)DD, 1, invD2, s->tau_fom);
+  else big_fom_kernel<<<1, 256, 0, st>>>(C0, Xi, (int)DD, 0, invD2, s->tau_fom);
+  BIG_COUNT();
+  // W_0 = Xi C_0' (- C_0' Xi)
+  p.A = bmat(Xi, 0); p.B = bmat(C0, 0); p.out[0] = eout(bmat(W, 0)); if ((rc = big_gemm(s, 0, 1, p, st, err, stats))) return rc;
+  if (!U) {
+    p.A = bmat(C0, 0); p.B = bmat(Xi, 0); p.out[0] = eout(bmat(W, 0), -1.0); eaux(p.out[0], bmat(W, 0), 1.0);
+    if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
+  }
+  // chunk-boundary operators W[start_{c+1}] = T_c W[start_c] T_c'
+  for (int c = 0; c + 1 < Cn; c++) {
+    const double2* Tc = s->T + (size_t)c * DD;
+    double2* Win = W + (size_t)s->start[c] * DD;
+    double2* Wout = W + (size_t)(s->start[c] + s->len[c]) * DD;
+    GemmParams q{}; q.batch = 1; q.nout = 1;
+    q.A = bmat(Win, 0); q.B = bmat(Tc, 0); q.out[0] = eout(bmat(s->tmpF, 0)); if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
+    q.A = bmat(Tc, 0); q.B = bmat(s->tmpF, 0); q.out[0] = eout(bmat(Wout, 0)); if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+  }
+  // lock-step conjugation sweeps inside all chunks: W[t+1] = P_t W[t] P_t'
+  for (int j = 0; j < s->Lmax - 1; j++) {
+    const int* tF = s->tab4F + (size_t)j * Cn;
+    GemmParams q{}; q.batch = Cn; q.nout = 1;
+    q.A = bmat(W, sd, tF); q.B = bmat(P, sd, tF); q.out[0] = eout(bmat(s->tmpF, sd));
+    if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
+    q.A = bmat(P, sd, tF); q.B = bmat(s->tmpF, sd); q.out[0] = eout(bmat(W, sd, tF, 1));
+    if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+  }
+  if (d.K > 0) {
+    BigTraceParams tp;
+    tp.W = W; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
+    tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.g = s->gk; tp.exact = 0; tp.invD2 = 0.0;
+    big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
+    BIG_COUNT();
+  }
+  return QOC_OK;
+}
+
 static int big_eval_member(BigState* s, int k, const double* x_dev, int want_grad, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   const size_t DD = s->DD; const long sd = (long)DD;
@@ -402,6 +486,7 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
   if ((rc = big_propagators_phase(s, k, x_dev, st, err, stats))) return rc;
   double2 *P = s->Pfinal, *S = s->exact ? s->xbuf[0] : s->buf[1], *C = s->exact ? s->xbuf[1] : s->buf[2], *W = s->buf[3];
   if ((rc = big_chunk_totals(s, st, err, stats))) return rc;
+  if (s->herm && !s->exact && want_grad) return big_eval_member_unitary(s, k, st, err, stats);
   // ---- phase 3: boundary states (stream sA) and boundary costates (stream sB), short sequential chains ----
   BIG_CUDA(cudaMemcpyAsync(S, s->Xi + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
   BIG_CUDA(cudaMemcpyAsync(C + (size_t)N * DD, s->Xt + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
