@@ -335,8 +335,18 @@ def main():
             tc = time.perf_counter() - t0
             cpu_baseline = {"value": 1.0 / (tc * M / ms_n), "unit": UNIT, "cores": threads, "kind": "port",
                             "sample": f"{ms_n} of {M} members, all {N} slices, C restatement of the reference loop order with OpenMP over members (the Julia reference is serial); scaled x{M / ms_n:g}"}
-            with qoc.GrapeEvaluator(sm, cfg["T"], N, cfg["sys_type"], wts=sw, gradient=cfg["gradient"], device=local_rank) as ev2:
-                Fg, Gg = ev2.eval(cfg["x"])
+            # the parity sample has few chains: force the execution strategy of the timed run (fused, one warp per chain)
+            saved = {k: os.environ.get(k) for k in ("QOC_PHASED", "QOC_CHUNKED")}
+            os.environ["QOC_PHASED"] = "0"; os.environ["QOC_CHUNKED"] = "0"
+            try:
+                with qoc.GrapeEvaluator(sm, cfg["T"], N, cfg["sys_type"], wts=sw, gradient=cfg["gradient"], device=local_rank) as ev2:
+                    Fg, Gg = ev2.eval(cfg["x"])
+            finally:
+                for k, v in saved.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
         else:
             ns = min(N, 100 if D <= 16 else 16)
             xsmp = cfg["x"][:, :ns]

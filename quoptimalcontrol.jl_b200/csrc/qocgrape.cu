@@ -31,6 +31,8 @@ struct qoc_handle {
   double2 *storeP2 = nullptr, *stS = nullptr, *stC = nullptr, *totT = nullptr, *totTt = nullptr;
   double* tau = nullptr;
   int chunked = 0;                       // chunk-parallel fused mode (150..1500 chains)
+  int chunked_closed = 0;                // >= 1500 chains: chunking (Cn = 4) only pays with the closed-system recursion
+  int unitary_fast = 1;                  // closed-system conjugation kernel when the problem is Hermitian (QOC_UNITARY_FAST=0 disables)
   double2 *bS = nullptr, *bC = nullptr;
   int NK = 0, red_chunk = 0, red_nchunks = 0;
   bool system_set = false;
@@ -150,6 +152,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     //   150..1499 chains      chunk-parallel fused: each chain split into Cn chunks (full occupancy)
     //   < 150 chains          fully slice-parallel pipeline with a chunked prefix scan (small_phased.cuh)
     // Short pulses stay on the plain fused kernel.
+    if (const char* e = getenv("QOC_UNITARY_FAST")) h->unitary_fast = atoi(e) != 0;
     h->phased = h->n_groups < 150 && d.N >= 32;
     h->chunked = !h->phased && h->n_groups < 1500 && d.N >= 64;
     if (const char* e = getenv("QOC_PHASED")) { h->phased = atoi(e) != 0; if (h->phased) h->chunked = 0; }
@@ -160,6 +163,13 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
       h->have_P = 0;
       h->Cn = std::max(2, std::min((8192 + h->n_groups - 1) / h->n_groups, std::max(2, d.N / 16)));   // ~8192 warps measured best
       if (const char* e = getenv("QOC_CHUNKS")) h->Cn = std::max(2, std::min(atoi(e), d.N));
+      h->Cn = std::min(h->Cn, d.N / 2);              // every chunk needs at least two slices
+      if (h->Cn < 2) { h->chunked = 0; h->Cn = 1; }
+    }
+    // with the closed-system recursion (6 products per slice in either mode) 4 chunks per chain still win at full batch:
+    // cfg4 4096 chains 2.44 ms vs 2.52 ms fused, 2048 chains 1.26 vs 1.50 ms
+    if (!h->phased && !h->chunked && h->n_groups >= 1500 && d.N >= 64 && d.gradient == QOC_GRAD_FIRST_ORDER && !getenv("QOC_CHUNKED")) {
+      h->chunked_closed = 1; h->Cn = 4;
     }
     if (h->phased) {
       h->have_P = 1;
@@ -179,7 +189,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     CR(dev_alloc(h, &h->ident, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->storeP, (size_t)h->n_groups * d.N * E));
     if (!h->phased) CR(dev_alloc(h, &h->storeS, (size_t)h->n_groups * d.N * E));
-    if (h->chunked) {
+    if (h->chunked || h->chunked_closed) {
       CR(dev_alloc(h, &h->totT, (size_t)h->n_groups * h->Cn * E));
       CR(dev_alloc(h, &h->totTt, (size_t)h->n_groups * h->Cn * E));
       CR(dev_alloc(h, &h->bS, (size_t)h->n_groups * (h->Cn + 1) * E));
@@ -341,7 +351,7 @@ static SmallParams small_params(qoc_handle* h, const double* x_dev) {
   p.dt = d.T / d.N; p.theta = d.expm_theta;
   p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev;
   p.storeP = h->storeP; p.storeS = h->storeS; p.fomc = h->fomc; p.gradc = h->gradc; p.out_final = nullptr;
-  p.Cn = 1; p.bS = nullptr; p.bC = nullptr; p.tau_in = nullptr;
+  p.Cn = 1; p.bS = nullptr; p.bC = nullptr; p.tau_in = nullptr; p.ident = h->ident;
   return p;
 }
 static SliceParams slice_params(qoc_handle* h, const double* x_dev) {
@@ -359,6 +369,19 @@ static int launch_chain(qoc_handle* h, const SmallParams& p, int sys, int grad, 
   fn<<<(unsigned)(((long)h->n_groups * (p.Cn > 1 ? p.Cn : 1) + 3) / 4), 128, h->smem_bytes, st>>>(p);
   return launch_check(h, "chain_kernel");
 }
+// closed-system kernel (Hermitian drift and controls, first-order gradient, fused mode)
+static int launch_chain_unitary(qoc_handle* h, const SmallParams& p, int sys, cudaStream_t st) {
+  chain_fn fn;
+  const bool u = sys == SYS_UNITARY;
+  if (h->NB == 2) fn = u ? chain_unitary_kernel<2, 1, SYS_UNITARY> : chain_unitary_kernel<2, 1, SYS_DENSITY>;
+  else if (h->CPW == 4) fn = u ? chain_unitary_kernel<1, 4, SYS_UNITARY> : chain_unitary_kernel<1, 4, SYS_DENSITY>;
+  else if (h->CPW == 2) fn = u ? chain_unitary_kernel<1, 2, SYS_UNITARY> : chain_unitary_kernel<1, 2, SYS_DENSITY>;
+  else fn = u ? chain_unitary_kernel<1, 1, SYS_UNITARY> : chain_unitary_kernel<1, 1, SYS_DENSITY>;
+  if (h->smem_bytes > 48 * 1024)
+    QOC_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+  fn<<<(unsigned)((h->n_groups + 3) / 4), 128, h->smem_bytes, st>>>(p);
+  return launch_check(h, "chain_unitary_kernel");
+}
 static int launch_slices(qoc_handle* h, const SliceParams& s, cudaStream_t st) {
   long warps = (long)h->n_groups * h->d.N;
   pick_slices(h->NB, h->CPW)<<<(unsigned)((warps + 3) / 4), 128, h->tb_bytes, st>>>(s);
@@ -373,7 +396,7 @@ static PhasedParams phased_params(qoc_handle* h, const double* x_dev) {
   p.fom_exact = d.gradient == QOC_GRAD_EXACT; p.theta = d.expm_theta;
   p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev; p.storePt = h->storeP; p.storeP = h->storeP2; p.stS = h->stS; p.stC = h->stC;
   p.totT = h->totT; p.totTt = h->totTt; p.tau = h->tau; p.fomc = h->fomc; p.gradc = h->gradc;
-  p.bS = h->bS; p.bC = h->bC; p.sys_in_smem = 0;
+  p.bS = h->bS; p.bC = h->bC; p.sys_in_smem = 0; p.store_plain = 0;
   return p;
 }
 
@@ -430,8 +453,26 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
   else if (h->CPW == 2) { k1 = chunk_expm_kernel<1, 2>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 2, SYS_UNITARY> : boundary2_kernel<1, 2, SYS_DENSITY>; }
   else { k1 = chunk_expm_kernel<1, 1>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 1, SYS_UNITARY> : boundary2_kernel<1, 1, SYS_DENSITY>; }
   if (smem1 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+  const bool closed = grad == GRAD_FIRST && h->herm && h->unitary_fast;     // closed-system conjugation recursion
+  p.store_plain = closed;
   k1<<<(unsigned)(((long)h->n_groups * h->Cn + 3) / 4), 128, smem1, st>>>(p);
   if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
+  if (closed) {
+    kfn kb, ks;
+    const bool u = sys == SYS_UNITARY;
+    if (h->NB == 2) { kb = u ? boundary_unitary_kernel<2, 1, SYS_UNITARY> : boundary_unitary_kernel<2, 1, SYS_DENSITY>; ks = sweep_unitary_kernel<2, 1>; }
+    else if (h->CPW == 4) { kb = u ? boundary_unitary_kernel<1, 4, SYS_UNITARY> : boundary_unitary_kernel<1, 4, SYS_DENSITY>; ks = sweep_unitary_kernel<1, 4>; }
+    else if (h->CPW == 2) { kb = u ? boundary_unitary_kernel<1, 2, SYS_UNITARY> : boundary_unitary_kernel<1, 2, SYS_DENSITY>; ks = sweep_unitary_kernel<1, 2>; }
+    else { kb = u ? boundary_unitary_kernel<1, 1, SYS_UNITARY> : boundary_unitary_kernel<1, 1, SYS_DENSITY>; ks = sweep_unitary_kernel<1, 1>; }
+    kb<<<(unsigned)((h->n_groups + 3) / 4), 128, h->tb_bytes, st>>>(p);
+    if ((rc = launch_check(h, "boundary_unitary_kernel")) != QOC_OK) return rc;
+    const size_t bbytes = (size_t)4 * h->d.K * E * sizeof(double2);
+    p.sys_in_smem = bbytes <= 96 * 1024;
+    const int smem3 = p.sys_in_smem ? (int)bbytes : 0;
+    if (smem3 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    ks<<<(unsigned)(((long)h->n_groups * h->Cn + 3) / 4), 128, smem3, st>>>(p);
+    return launch_check(h, "sweep_unitary_kernel");
+  }
   k2<<<(unsigned)((h->n_groups * 2 + 3) / 4), 128, 0, st>>>(p);
   if ((rc = launch_check(h, "boundary2_kernel")) != QOC_OK) return rc;
   cp.Cn = h->Cn; cp.bS = h->bS; cp.bC = h->bC; cp.tau_in = h->tau; cp.have_P = 1;
@@ -448,8 +489,10 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if (h->phased && want_grad) {
     if ((rc = eval_phased(h, x_dev, sys, grad, st)) != QOC_OK) return rc;
-  } else if (h->chunked && want_grad) {
+  } else if ((h->chunked || (h->chunked_closed && h->herm && h->unitary_fast)) && want_grad) {
     if ((rc = eval_chunked(h, p, x_dev, sys, grad, st)) != QOC_OK) return rc;
+  } else if (grad == GRAD_FIRST && h->herm && !h->have_P && h->unitary_fast) {
+    if ((rc = launch_chain_unitary(h, p, sys, st)) != QOC_OK) return rc;
   } else {
     if (h->have_P) {
       SliceParams s = slice_params(h, x_dev);

@@ -54,6 +54,7 @@ struct SmallParams {
   const double2* bS;   // [n_groups][Cn+1][E]
   const double2* bC;   // [n_groups][Cn+1][E]
   const double* tau_in;  // [n_groups][CPW][2]
+  const double2* ident;  // packed identity (closed-system kernel)
 };
 
 template <int NB> __host__ __device__ constexpr int cm_elems() { return NB * NB * 2 * 32; }  // double2 per packed matrix
@@ -180,7 +181,7 @@ template <int CPW> struct Slot {
 };
 
 // write the 8-chunked, group-reduced gradient values of slice t: out[c] = Re sum mats_c .* W
-template <int NB, int CPW, bool SH>
+template <int NB, int CPW, bool SH, bool CONJM = false>
 __device__ __forceinline__ void emit_gradient(const SmallParams& p, const Lane& L, const Slot<CPW>& sl,
                                               const double2* mats, const CM<NB>& W, int t) {
   constexpr int GS = 32 / CPW;
@@ -189,7 +190,8 @@ __device__ __forceinline__ void emit_gradient(const SmallParams& p, const Lane& 
     double v[8];
 #pragma unroll
     for (int c = 0; c < 8; c++)
-      v[c] = (c0 + c < p.K) ? cm_redot_partial<NB, SH>(L, mats + (size_t)(c0 + c) * cm_elems<NB>(), W) : 0.0;
+      v[c] = (c0 + c < p.K) ? (CONJM ? cm_redotc_partial<NB, SH>(L, mats + (size_t)(c0 + c) * cm_elems<NB>(), W)
+                                     : cm_redot_partial<NB, SH>(L, mats + (size_t)(c0 + c) * cm_elems<NB>(), W)) : 0.0;
     group_sum8<GS>(L.lane, v);
     int within = L.lane % GS;
     int idx = (within * 8) / GS;
@@ -382,6 +384,105 @@ __global__ void __launch_bounds__(128, (NB == 1 && GRAD != GRAD_EXACT) ? QOC_CHA
   extern __shared__ double2 smem[];
   if (p.sys_in_smem) chain_body<NB, CPW, SYS, GRAD, true>(p, smem);
   else chain_body<NB, CPW, SYS, GRAD, false>(p, smem);
+}
+
+// From U_N^T: C_0 = U_N' Xt (U_N), the overlap tau, the figure of merit and the scaled, sign-prepared starting operator
+//   W = -f W_0,  W_0 = Xi C_0' (- C_0' Xi),  f = gradient scalar with i/dt folded in,
+// such that the gradient of slice t is  sum conj(B~_c) .* W_t  (for Hermitian B the transposed scaled control is -conj(B~)).
+// XiP / XtP are the packed states (unitary: transposed, density: as is).
+template <int NB, int CPW, int SYS>
+__device__ __forceinline__ CM<NB> unitary_w0(const Lane& L, const CM<NB>& Ut, const CM<NB>& XiP, const CM<NB>& XtP,
+                                             int sign_static, double invD2, double* tb, double& fom) {
+  constexpr int GS = 32 / CPW;
+  double tr_, ti_;
+  if (SYS == SYS_UNITARY) {
+    const CM<NB> C0 = mul_nt<NB, true, false>(Ut, XtP);         // conj(U^T) Xt = U' Xt
+    const CM<NB> Xi = transpose<NB>(L, XiP, tb);
+    cm_dotc_partial<NB>(Xi, C0, tr_, ti_);                      // tau = tr(S_N' Xt) = tr(Xi' C_0)
+    tr_ = group_sum<GS>(tr_); ti_ = group_sum<GS>(ti_);
+    fom = tr_ * tr_ - ti_ * ti_;                                // Re(tau*tau)          (cost_functions.jl:99-101)
+    const CM<NB> W0 = mul_nt<NB, false, true>(Xi, C0);          // Xi C_0'
+    const double sg = 2.0 * sign_static;                        // -f,  f = 2(+-i dt) tau (i/dt) = -+2 tau
+    return cm_cscale<NB>(W0, sg * tr_, sg * ti_);
+  }
+  const CM<NB> Zt = mul_nt<NB>(Ut, XtP);                        // U^T Xt^T = (Xt U)^T
+  const CM<NB> C0 = mul_nt<NB, true, false>(Ut, Zt);            // U' Xt U
+  cm_dotc_partial<NB>(C0, XiP, tr_, ti_);                       // tau = tr(Xt' S_N) = tr(C_0' Xi)
+  tr_ = group_sum<GS>(tr_); ti_ = group_sum<GS>(ti_);
+  fom = 1.0 - (tr_ * tr_ + ti_ * ti_) * invD2;                  // C1                    (cost_functions.jl:13-17)
+  const CM<NB> C0t = transpose<NB>(L, C0, tb);
+  const CM<NB> Xit = transpose<NB>(L, XiP, tb);
+  CM<NB> W0 = mul_nt<NB, false, true>(XiP, C0);                 // Xi C_0'
+  mul_nt_acc<NB, true, false>(cm_neg<NB>(C0t), Xit, W0);        // - C_0' Xi
+  return W0;                                                    // -f W_0 with f = (i dt)(i/dt) = -1
+}
+
+// Closed systems (Hermitian drift and controls, first-order gradient): every P_t is unitary, so V_t = U_N U_t' and the
+// gradient operator is a conjugation,  W_t = S_t C_t' (- C_t' S_t) = U_t W_0 U_t',  W_0 = Xi C_0' (- C_0' Xi),
+// C_0 = U_N' Xt (U_N).  Pass 1 computes and stores only P_t while accumulating U_N^T; pass 2 runs W <- P W P' with the
+// trace-dots.  Per slice: the same 6 products, ONE transpose (inside expm) instead of four, 2 KB of HBM traffic instead of
+// 4 KB, and no state store.  For Hermitian B the transposed scaled control is -conj(B~), so no extra matrices are needed.
+template <int NB, int CPW, int SYS, bool SH>
+__device__ __forceinline__ void chain_body_unitary(const SmallParams& p, double2* smem) {
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int w = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  if (w >= p.n_groups) return;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int GS = 32 / CPW;
+  constexpr int E = cm_elems<NB>();
+  constexpr int TBW = NB * NB * 2 * TB_PLANE;
+  const float theta = (float)p.theta;
+  const int K = p.K, N = p.N;
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)warp_in_cta * TBW;
+  const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
+  if (SH) {
+    double2* mine = smem + (size_t)(blockDim.x >> 5) * TBW / 2 + (size_t)warp_in_cta * p.nmat * E;
+    for (int i = L.lane; i < p.nmat * E; i += 32) mine[i] = sysw[i];
+    __syncwarp();
+    sysw = mine;
+  }
+  const double* xr = p.x + (size_t)sl.r * N * K;
+  double2* stP = p.storeP + (size_t)w * N * E;
+  const double invD2 = 1.0 / ((double)p.D * (double)p.D);
+  double xpre[XPF];
+  auto prefetch_x = [&](int t) {
+#pragma unroll
+    for (int j = 0; j < XPF; j++) xpre[j] = (j < K) ? __ldg(xr + (size_t)t * K + j) : 0.0;
+  };
+  // ---------------- pass 1: propagators and U_N^T = P_0^T P_1^T ... ----------------
+  CM<NB> Ut = cm_load<NB>(L, p.ident + (size_t)sl.sysgroup * E);
+  prefetch_x(0);
+  for (int t = 0; t < N; t++) {
+    const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
+    if (t + 1 < N) prefetch_x(t + 1);
+    const CM<NB> P = expm_t8<NB>(L, G, theta, true, tb);
+    cm_store<NB>(L, stP + (size_t)t * E, P);
+    Ut = mul_nt<NB>(Ut, P);                                     // U_{t+1}^T = U_t^T P_t^T
+  }
+  // ---------------- C_0, overlap, figure of merit, W_0 ----------------
+  double fom;
+  CM<NB> W = unitary_w0<NB, CPW, SYS>(L, Ut, cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E), cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E),
+                                     p.sign_static, invD2, tb, fom);
+  if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
+  // ---------------- pass 2: conjugation recursion with the trace-dots ----------------
+  const double2* Bmats = sysw + E;
+  CM<NB> Pn = cm_load<NB>(L, stP);
+  for (int t = 0; t < N; t++) {
+    const CM<NB> P = Pn;
+    if (t + 1 < N) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
+    emit_gradient<NB, CPW, SH, true>(p, L, sl, Bmats, W, t);
+    if (t + 1 < N) {
+      const CM<NB> X = mul_nt<NB, true, false>(P, W);           // conj(P) W^T = (W P')^T
+      W = mul_nt<NB>(P, X);                                     // P W P'
+    }
+  }
+}
+template <int NB, int CPW, int SYS>
+__global__ void __launch_bounds__(128, NB == 1 ? QOC_CHAIN_MINB : 1) chain_unitary_kernel(const SmallParams p) {
+  extern __shared__ double2 smem[];
+  if (p.sys_in_smem) chain_body_unitary<NB, CPW, SYS, true>(p, smem);
+  else chain_body_unitary<NB, CPW, SYS, false>(p, smem);
 }
 
 // Slice-parallel propagators: one warp per (system group / pulse, slice).  Writes the packed TRANSPOSED

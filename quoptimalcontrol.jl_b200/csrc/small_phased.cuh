@@ -31,6 +31,7 @@ struct PhasedParams {
   double2* bS;             // [n_groups][Cn+1][E] chunk-boundary states   (chunk-parallel fused mode)
   double2* bC;             // [n_groups][Cn+1][E] chunk-boundary costates
   int sys_in_smem;
+  int store_plain;         // chunk_expm_kernel stores P_t instead of P_t^T (closed-system mode)
   double* fomc;
   double* gradc;
 };
@@ -270,7 +271,7 @@ __device__ __forceinline__ void chunk_expm_body(const PhasedParams& p, double2* 
     }
     const CM<NB> P = expm_t8<NB>(L, G, (float)p.theta, p.herm, tb);
     const CM<NB> Pt = transpose<NB>(L, P, tb);
-    cm_store<NB>(L, stP + (size_t)t * E, Pt);
+    cm_store<NB>(L, stP + (size_t)t * E, p.store_plain ? P : Pt);
     Tt = (t == t0) ? Pt : mul_nt<NB>(Tt, P);
   }
   cm_store<NB>(L, p.totTt + ((size_t)w * p.Cn + c) * E, Tt);
@@ -327,6 +328,72 @@ __global__ void __launch_bounds__(128) boundary2_kernel(const PhasedParams p) {
       cm_store<NB>(L, st + (size_t)c * E, C);
     }
   }
+}
+
+// ---- chunk-parallel closed-system mode: K1 = chunk_expm (stores P, not P^T), K2u, K3u ---------------------------
+// K2u: one warp per group: U_N^T from the chunk totals, W_0 (unitary_w0), then the chunk-boundary operators
+//      bW[c+1] = T_c bW[c] T_c'  (stored in the bS buffer).
+template <int NB, int CPW, int SYS>
+__global__ void __launch_bounds__(128) boundary_unitary_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= p.n_groups) return;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int GS = 32 / CPW;
+  constexpr int E = cm_elems<NB>();
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
+  const int Cn = p.Cn;
+  const double2* T = p.totT + (size_t)w * Cn * E;
+  CM<NB> Ut = transpose<NB>(L, cm_load<NB>(L, T), tb);                        // U^T after chunk 0
+  for (int c = 1; c < Cn; c++) Ut = mul_nt<NB>(Ut, cm_load<NB>(L, T + (size_t)c * E));   // U^T T_c^T
+  double fom;
+  CM<NB> W = unitary_w0<NB, CPW, SYS>(L, Ut, cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E), cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E),
+                                     p.sign_static, 1.0 / ((double)p.D * (double)p.D), tb, fom);
+  if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
+  double2* bW = p.bS + (size_t)w * (Cn + 1) * E;
+  cm_store<NB>(L, bW, W);
+  for (int c = 0; c + 1 < Cn; c++) {
+    const CM<NB> Tc = cm_load<NB>(L, T + (size_t)c * E);
+    const CM<NB> X = mul_nt<NB, true, false>(Tc, W);
+    W = mul_nt<NB>(Tc, X);
+    cm_store<NB>(L, bW + (size_t)(c + 1) * E, W);
+  }
+}
+// K3u: warp (w, c): conjugation recursion over the chunk's slices with the trace-dots.
+template <int NB, int CPW, bool SH>
+__device__ __forceinline__ void sweep_unitary_body(const PhasedParams& p, double2* smem) {
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
+  if (gw >= p.n_groups * p.Cn) return;
+  const int w = gw / p.Cn, c = gw - w * p.Cn;
+  const Lane L(threadIdx.x & 31);
+  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  constexpr int E = cm_elems<NB>();
+  const int N = p.N, K = p.K;
+  const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
+  const double2* Bmats = p.sys + (size_t)sl.sysgroup * p.nmat * E + E;
+  if (SH) {
+    double2* mine = smem + (size_t)warp_in_cta * K * E;
+    for (int i = L.lane; i < K * E; i += 32) mine[i] = Bmats[i];
+    __syncwarp();
+    Bmats = mine;
+  }
+  SmallParams sp; sp.M = p.M; sp.N = N; sp.K = K; sp.gradc = p.gradc;
+  const double2* stP = p.storePt + (size_t)w * N * E;      // holds P (not P^T) in this mode
+  CM<NB> W = cm_load<NB>(L, p.bS + ((size_t)w * (p.Cn + 1) + c) * E);
+  CM<NB> Pn = cm_load<NB>(L, stP + (size_t)t0 * E);
+  for (int t = t0; t < t1; t++) {
+    const CM<NB> P = Pn;
+    if (t + 1 < t1) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
+    emit_gradient<NB, CPW, SH, true>(sp, L, sl, Bmats, W, t);
+    if (t + 1 < t1) { const CM<NB> X = mul_nt<NB, true, false>(P, W); W = mul_nt<NB>(P, X); }
+  }
+}
+template <int NB, int CPW>
+__global__ void __launch_bounds__(128, NB == 1 ? 5 : 1) sweep_unitary_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  if (p.sys_in_smem) sweep_unitary_body<NB, CPW, true>(p, smem); else sweep_unitary_body<NB, CPW, false>(p, smem);
 }
 
 }  // namespace qoc

@@ -203,6 +203,20 @@ template <int NB> __device__ __forceinline__ void cm_dotc_partial(const CM<NB>& 
   }
 }
 // per-lane partial of Re sum_ab M[a][b] * X[a][b] with M in packed storage
+// per-lane partial of Re sum_ab conj(M[a][b]) * X[a][b]
+template <int NB, bool SH> __device__ __forceinline__ double cm_redotc_partial(const Lane& L, const double2* m, const CM<NB>& x) {
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      double2 r = ld_packed<SH>(m + ((i * NB + j) * 2 + 0) * 32 + L.lane);
+      double2 c = ld_packed<SH>(m + ((i * NB + j) * 2 + 1) * 32 + L.lane);
+      s = fma(r.x, x.re[i][j][0], s); s = fma(c.x, x.im[i][j][0], s);
+      s = fma(r.y, x.re[i][j][1], s); s = fma(c.y, x.im[i][j][1], s);
+    }
+  return s;
+}
 template <int NB, bool SH> __device__ __forceinline__ double cm_redot_partial(const Lane& L, const double2* m, const CM<NB>& x) {
   double s = 0;
 #pragma unroll
