@@ -45,6 +45,10 @@ struct qoc_handle {
   long long ws_bytes = 0;
   qoc_stats st{};
   BigState* big = nullptr;
+  // CUDA-graph replay of the whole qoc_eval sequence (small path): [0] value only, [1] value + gradient
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  int graph_launches[2] = {0, 0};
+  bool use_graph = true, in_capture = false;
   // one-shot NVLink all-reduce (qoc_comm_*)
   char* comm_local = nullptr;            // this rank's exchange buffer: data[2][n] doubles, then flags[2][QOC_MAX_RANKS]
   char* comm_peer_host[QOC_MAX_RANKS] = {};
@@ -153,6 +157,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     //   < 150 chains          fully slice-parallel pipeline with a chunked prefix scan (small_phased.cuh)
     // Short pulses stay on the plain fused kernel.
     if (const char* e = getenv("QOC_UNITARY_FAST")) h->unitary_fast = atoi(e) != 0;
+    if (const char* e = getenv("QOC_GRAPH")) h->use_graph = atoi(e) != 0;
     h->phased = h->n_groups < 150 && d.N >= 32;
     h->chunked = !h->phased && h->n_groups < 1500 && d.N >= 64;
     if (const char* e = getenv("QOC_PHASED")) { h->phased = atoi(e) != 0; if (h->phased) h->chunked = 0; }
@@ -234,6 +239,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->big) big_destroy(h->big);
+  for (auto& g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
   for (int r = 0; r < h->comm_world; r++) if (r != h->comm_rank && h->comm_peer_host[r]) cudaIpcCloseMemHandle(h->comm_peer_host[r]);
   if (h->comm_local) cudaFree(h->comm_local);
   if (h->comm_peers) cudaFree(h->comm_peers);
@@ -486,7 +492,7 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   const int sys = d.sys_type == QOC_UNITARY_GATE ? SYS_UNITARY : SYS_DENSITY;
   const int grad = !want_grad ? GRAD_NONE : (d.gradient == QOC_GRAD_EXACT ? GRAD_EXACT : GRAD_FIRST);
   const int slot = h->kring_count % qoc_handle::KRING;
-  QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
+  if (!h->in_capture) QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if (h->phased && want_grad) {
     if ((rc = eval_phased(h, x_dev, sys, grad, st)) != QOC_OK) return rc;
   } else if ((h->chunked || (h->chunked_closed && h->herm && h->unitary_fast)) && want_grad) {
@@ -501,8 +507,7 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
     }
     if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
   }
-  QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st));
-  h->kring_count++;
+  if (!h->in_capture) { QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st)); h->kring_count++; }
   dim3 g1((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R), h->red_nchunks);
   reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->part, d.M, h->NK, h->red_chunk, h->red_nchunks);
   if ((rc = launch_check(h, "reduce_members_pass1")) != QOC_OK) return rc;
@@ -526,6 +531,41 @@ extern "C" int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_de
   return eval_device_on(h, x_dev, FG_dev, want_gradient, (cudaStream_t)stream);   // NULL = CUDA default stream
 }
 
+// D2H of the result rows: everything when the gradient was asked for, else only the F column
+static cudaError_t copy_result_async(qoc_handle* h, bool grad) {
+  const size_t row = (size_t)h->NK + 1;
+  if (grad) return cudaMemcpyAsync(h->hout, h->out, (size_t)h->d.R * row * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+  return cudaMemcpy2DAsync(h->hout, row * sizeof(double), h->out, row * sizeof(double), sizeof(double), h->d.R, cudaMemcpyDeviceToHost, h->stream);
+}
+
+// Captures H2D(x) -> kernels -> D2H([F|G]) once per variant and replays it afterwards: one graph launch per
+// evaluation.  Everything in the sequence is static (pinned staging buffers, device buffers, launch geometry).
+static bool eval_via_graph(qoc_handle* h, bool grad) {
+  const int gi = grad ? 1 : 0;
+  const size_t nx = (size_t)h->d.R * h->NK;
+  if (!h->graph_exec[gi]) {
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    h->in_capture = true;
+    const long long before = h->st.n_launches;
+    bool ok = cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+    ok = ok && eval_small(h, h->x, h->out, grad, h->stream) == QOC_OK;
+    ok = ok && copy_result_async(h, grad) == cudaSuccess;
+    h->in_capture = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    h->graph_launches[gi] = (int)(h->st.n_launches - before);
+    h->st.n_launches = before;
+    if (!ok || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return false; }
+    e = cudaGraphInstantiate(&h->graph_exec[gi], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { h->graph_exec[gi] = nullptr; cudaGetLastError(); return false; }
+  }
+  if (cudaGraphLaunch(h->graph_exec[gi], h->stream) != cudaSuccess) { cudaGetLastError(); return false; }
+  h->st.n_launches += h->graph_launches[gi];
+  h->st.launches_last_eval = h->graph_launches[gi];
+  return cudaStreamSynchronize(h->stream) == cudaSuccess;
+}
+
 extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
   if (!h) return QOC_EINVAL;
   if (!x) { h->err = "qoc_eval: null pulse"; return QOC_EINVAL; }
@@ -534,20 +574,24 @@ extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
   QOC_CUDA(h, cudaSetDevice(d.device));
   const size_t nx = (size_t)d.R * h->NK;
   memcpy(h->hx, x, nx * sizeof(double));
-  QOC_CUDA(h, cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  QOC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  int rc = eval_device_on(h, h->x, h->out, G != nullptr, h->stream);
-  if (rc != QOC_OK) return rc;
-  QOC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   const size_t row = (size_t)h->NK + 1;
-  if (G) {
-    QOC_CUDA(h, cudaMemcpyAsync(h->hout, h->out, (size_t)d.R * row * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  } else {
-    QOC_CUDA(h, cudaMemcpy2DAsync(h->hout, row * sizeof(double), h->out, row * sizeof(double), sizeof(double), d.R,
-                                  cudaMemcpyDeviceToHost, h->stream));
+  bool done = false;
+  if (h->path == 1 && h->use_graph) {
+    h->st.n_evals++;
+    done = eval_via_graph(h, G != nullptr);
+    if (!done) { h->use_graph = false; h->st.n_evals--; h->in_capture = false; }   // capture unavailable: plain launches from now on
+    else h->st.gpu_ms_last_eval = 0.f;
   }
-  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
-  QOC_CUDA(h, cudaEventElapsedTime(&h->st.gpu_ms_last_eval, h->ev0, h->ev1));
+  if (!done) {
+    QOC_CUDA(h, cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    QOC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int rc = eval_device_on(h, h->x, h->out, G != nullptr, h->stream);
+    if (rc != QOC_OK) return rc;
+    QOC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QOC_CUDA(h, copy_result_async(h, G != nullptr));
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+    QOC_CUDA(h, cudaEventElapsedTime(&h->st.gpu_ms_last_eval, h->ev0, h->ev1));
+  }
   for (int r = 0; r < d.R; r++) {
     if (F) F[r] = h->hout[r * row];
     if (G) memcpy(G + (size_t)r * h->NK, h->hout + r * row + 1, sizeof(double) * h->NK);
