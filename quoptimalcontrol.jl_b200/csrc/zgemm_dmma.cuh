@@ -42,8 +42,6 @@ struct GemmParams {
   int nout;
   const int* s_ptr;     // device scalar: scaling power of the exponential (may be null -> 0)
   const double* cz_ptr; // device complex scalar (re, im) for the cz coefficient modes (may be null)
-  const int* skip_ge;   // optional device scalar: if non-null and *skip_ge <= skip_level the launch is a no-op
-  int skip_level;
 };
 
 __device__ __forceinline__ const double2* bm_ptr(const BatchedMat& m, int b, bool& idle) {
@@ -66,7 +64,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <int OPA, int OPB>
 __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmParams p) {
   extern __shared__ double2 gsm[];
-  if (p.skip_ge && *p.skip_ge <= p.skip_level) return;
   const int b = blockIdx.y;
   bool idle = false;
   const double2* Ag = bm_ptr(p.A, b, idle);

@@ -231,3 +231,31 @@ def test_no_controls(D):
         F, G = ev.eval(x)
     Fo, Go = orc.fom_and_gradient_grape(A, [], x, T, Xi, Xt, orc.STATE_TRANSFER)
     assert abs(F - Fo) < 1e-12 and G.shape == (0, N)
+
+
+def test_c_abi_error_paths_and_stats():
+    """Status codes and messages through the raw C ABI (no Python-side validation in between)."""
+    import ctypes as C
+    lib = qoc._lib.load()
+    A, B, Xi, Xt = random_system(4, 2, seed=5)
+    h = C.c_void_p()
+    d = qoc._lib.QocDesc(sys_type=0, D=4, K=2, N=6, M=1, R=1, T=1.0, gradient=0, convention=0, device=0, expm_theta=0.0, flags=0)
+    assert lib.qoc_create(C.byref(h), C.byref(d)) == 0
+    x = np.zeros(12); F = np.zeros(1); G = np.zeros(12)
+    assert lib.qoc_eval(h, x.ctypes.data, F.ctypes.data, G.ctypes.data) == qoc._lib.QOC_EINVAL      # no system yet
+    assert b"qoc_set_system" in lib.qoc_last_error(h)
+    cm = lambda M_: np.ascontiguousarray(np.swapaxes(np.asarray(M_, dtype=complex), -1, -2))
+    a, b, xi, xt = cm(A), cm(B), cm(Xi), cm(Xt)
+    assert lib.qoc_set_system(h, None, b.ctypes.data, xi.ctypes.data, xt.ctypes.data, None, 0) == qoc._lib.QOC_EINVAL
+    assert lib.qoc_set_system(h, a.ctypes.data, b.ctypes.data, xi.ctypes.data, xt.ctypes.data, None, 0) == 0
+    assert lib.qoc_eval(h, None, F.ctypes.data, G.ctypes.data) == qoc._lib.QOC_EINVAL
+    assert lib.qoc_eval(h, x.ctypes.data, F.ctypes.data, None) == 0                                  # value only
+    assert lib.qoc_eval(h, x.ctypes.data, F.ctypes.data, G.ctypes.data) == 0
+    st = qoc._lib.QocStats()
+    assert lib.qoc_get_stats(h, C.byref(st)) == 0
+    assert st.n_evals == 2 and st.launches_last_eval >= 3 and st.path == 1 and st.workspace_bytes > 0
+    bad = qoc._lib.QocDesc(sys_type=0, D=4, K=2, N=6, M=1, R=1, T=1.0, device=99)
+    h2 = C.c_void_p()
+    assert lib.qoc_create(C.byref(h2), C.byref(bad)) == qoc._lib.QOC_EINVAL and not h2.value
+    assert lib.qoc_eval_allreduce_device(h, 1, 1, 1, None) == qoc._lib.QOC_EINVAL                   # comm not connected
+    assert lib.qoc_destroy(h) == 0
