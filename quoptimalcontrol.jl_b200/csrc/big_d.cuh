@@ -130,7 +130,7 @@ __global__ void big_accumulate_kernel(double* __restrict__ FG, const double* __r
 // ---------------------------------------------------------------------------------------------- host state
 struct BigState {
   qoc_desc d{};
-  int Dp = 0, Cn = 1, Lmax = 1, unitary = 0;
+  int Dp = 0, BT = 64, Cn = 1, Lmax = 1, unitary = 0;   // BT: CTA tile edge of the GEMM kernel (64, or 32 when that pads D tighter)
   size_t DD = 0;
   std::vector<int> start, len;
   cudaStream_t sA = nullptr, sB = nullptr;
@@ -185,12 +185,14 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
   *out = s;
   s->d = d;
   s->exact = d.gradient == QOC_GRAD_EXACT;
-  s->Dp = ((d.D + 63) / 64) * 64;
+  { const int d32 = ((d.D + 31) / 32) * 32; if (d32 % 64 == 32) { s->BT = 32; s->Dp = d32; } else { s->BT = 64; s->Dp = ((d.D + 63) / 64) * 64; } }
   s->DD = (size_t)s->Dp * s->Dp;
   s->unitary = d.sys_type == QOC_UNITARY_GATE;
   // chunking: (Dp/64)^2 tiles per GEMM; aim at one full wave of 2 CTAs/SM (296 CTAs) per lock-step launch
-  int tiles = (s->Dp / 64) * (s->Dp / 64);
+  int tiles = (s->Dp / s->BT) * (s->Dp / s->BT);
   int Cn = std::max(1, 296 / tiles);   // one full wave (2 CTAs/SM) per lock-step launch: measured best of {18, 37, 74} at D = 256
+  // small tiles counts: the 2*Cn sequential boundary launches would dominate; launches ~ 2 Cn + 3 N / Cn is minimal at sqrt(1.5 N)
+  Cn = std::min(Cn, std::max(1, (int)std::sqrt(1.5 * d.N)));
   if (const char* e = getenv("QOC_BIG_CHUNKS")) Cn = std::max(1, atoi(e));   // tuning override
   Cn = std::min(Cn, std::max(1, d.N / 2));
   s->Cn = Cn;
@@ -313,15 +315,25 @@ static inline void eaux(EpiOut& e, BatchedMat m, double coef, int pow2 = 0, int 
 
 static int big_gemm(BigState* s, int opA, int opB, GemmParams& p, cudaStream_t st, std::string& err, qoc_stats& stats) {
   typedef void (*kfn)(const GemmParams);
-  kfn fn = opA == 0 ? (opB == 0 ? zgemm_dmma_kernel<0, 0> : zgemm_dmma_kernel<0, 1>) : (opB == 0 ? zgemm_dmma_kernel<1, 0> : zgemm_dmma_kernel<1, 1>);
+  kfn fn;
+  int smem;
+  if (s->BT == 64) {
+    fn = opA == 0 ? (opB == 0 ? zgemm_dmma_kernel<0, 0, 4> : zgemm_dmma_kernel<0, 1, 4>) : (opB == 0 ? zgemm_dmma_kernel<1, 0, 4> : zgemm_dmma_kernel<1, 1, 4>);
+    smem = GemmGeom<4>::SMEM_BYTES;
+  } else {
+    fn = opA == 0 ? (opB == 0 ? zgemm_dmma_kernel<0, 0, 2> : zgemm_dmma_kernel<0, 1, 2>) : (opB == 0 ? zgemm_dmma_kernel<1, 0, 2> : zgemm_dmma_kernel<1, 1, 2>);
+    smem = GemmGeom<2>::SMEM_BYTES;
+  }
   if (!s->attr_set) {
-    kfn all[] = {zgemm_dmma_kernel<0, 0>, zgemm_dmma_kernel<0, 1>, zgemm_dmma_kernel<1, 0>, zgemm_dmma_kernel<1, 1>};
-    for (kfn f : all) BIG_CUDA(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_BYTES));
+    kfn all4[] = {zgemm_dmma_kernel<0, 0, 4>, zgemm_dmma_kernel<0, 1, 4>, zgemm_dmma_kernel<1, 0, 4>, zgemm_dmma_kernel<1, 1, 4>};
+    kfn all2[] = {zgemm_dmma_kernel<0, 0, 2>, zgemm_dmma_kernel<0, 1, 2>, zgemm_dmma_kernel<1, 0, 2>, zgemm_dmma_kernel<1, 1, 2>};
+    for (kfn f : all4) BIG_CUDA(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmGeom<4>::SMEM_BYTES));
+    for (kfn f : all2) BIG_CUDA(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmGeom<2>::SMEM_BYTES));
     s->attr_set = true;
   }
   p.D = s->Dp;
-  dim3 grid((s->Dp / 64) * (s->Dp / 64), p.batch);
-  fn<<<grid, GB_THREADS, GB_SMEM_BYTES, st>>>(p);
+  dim3 grid((s->Dp / s->BT) * (s->Dp / s->BT), p.batch);
+  fn<<<grid, GB_THREADS, smem, st>>>(p);
   BIG_CUDA(cudaGetLastError());
   stats.n_launches++; stats.launches_last_eval++;
   return QOC_OK;

@@ -1,7 +1,7 @@
 // Batched complex-FP64 GEMM on the FP64 tensor pipe (DMMA.8x8x4), for the large-dimension GRAPE path.
 //   C[b] = epilogue( op(A[b]) * op(B[b]) ),  op in {N, C = conjugate transpose},  square D x D, D % 64 == 0,
 //   interleaved (re, im) column-major matrices (the caller's own layout: Julia ComplexF64 arrays).
-// CTA tile 64 x 64 x 8, 256 threads = 8 warps of 32 x 16 complex outputs, 4-stage cp.async pipeline.
+// CTA tile 64 x 64 x 8 (or 32 x 32 x 8), 256 threads = 8 warps of 32 x 16 (16 x 8) complex outputs, 4-stage cp.async pipeline.
 // Operand tiles are staged in the orientation they have in global memory (so every cp.async moves a contiguous
 // run) with row strides chosen so that the 16-byte fragment loads are bank-conflict free:
 //   "KM" tile [k][mn], stride 66 (== 2 mod 8)   when the operand is contiguous along m / n
@@ -14,10 +14,17 @@
 
 namespace qoc {
 
-constexpr int GB_M = 64, GB_N = 64, GB_K = 8, GB_STAGES = 4, GB_THREADS = 256;
-constexpr int GB_LD_KM = 66, GB_LD_MK = 12;
-constexpr int GB_TILE_ELEMS = 768;                                  // max(8*66, 64*12) double2 per operand per stage
-constexpr int GB_SMEM_BYTES = GB_STAGES * 2 * GB_TILE_ELEMS * 16;   // 98304
+// Tile geometry: 8 warps as 2 (m) x 4 (n); each warp owns MI x NJ 8x8 blocks.  MI = 4, NJ = 2: CTA tile 64 x 64 (the
+// workhorse); MI = 2, NJ = 1: CTA tile 32 x 32, used when D pads tighter to a multiple of 32 (e.g. 5 qubits, D = 32).
+constexpr int GB_K = 8, GB_STAGES = 4, GB_THREADS = 256;
+constexpr int GB_LD_MK = 12;
+template <int MI> struct GemmGeom {
+  static constexpr int BT = 16 * MI;                 // CTA tile edge (square tiles: BN = 32 * NJ with NJ = MI / 2)
+  static constexpr int LD_KM = BT + 2;               // == 2 (mod 8)
+  static constexpr int TILE_ELEMS = (GB_K * LD_KM > BT * GB_LD_MK) ? GB_K * LD_KM : BT * GB_LD_MK;
+  static constexpr int SMEM_BYTES = GB_STAGES * 2 * TILE_ELEMS * 16;
+  static constexpr int LOADS = BT * GB_K / GB_THREADS;   // cp.async per thread per operand per stage (2 or 1)
+};
 
 // A batched matrix argument: matrix b lives at ptr + index(b) * stride, index(b) = table ? table[b] + offset : b.
 // A negative table entry means "this batch entry is idle in this launch" (ragged chunks).
@@ -61,9 +68,12 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
       : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <int OPA, int OPB>
+template <int OPA, int OPB, int MI>
 __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmParams p) {
   extern __shared__ double2 gsm[];
+  constexpr int NJ = MI / 2;
+  constexpr int GB_M = GemmGeom<MI>::BT, GB_N = GemmGeom<MI>::BT, GB_LD_KM = GemmGeom<MI>::LD_KM;
+  constexpr int GB_TILE_ELEMS = GemmGeom<MI>::TILE_ELEMS;
   const int b = blockIdx.y;
   bool idle = false;
   const double2* Ag = bm_ptr(p.A, b, idle);
@@ -74,14 +84,14 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
   const int m0 = (blockIdx.x / tiles_n) * GB_M, n0 = (blockIdx.x % tiles_n) * GB_N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;
+  const int wm0 = (warp >> 2) * (8 * MI), wn0 = (warp & 3) * (8 * NJ);
 
   // acc[i][j][c]: block row i (4), block col j (2), c = re0, re1, im0, im1
-  double acc[4][2][4];
+  double acc[MI][NJ][4];
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < MI; i++)
 #pragma unroll
-    for (int j = 0; j < 2; j++)
+    for (int j = 0; j < NJ; j++)
 #pragma unroll
       for (int c = 0; c < 4; c++) acc[i][j][c] = 0.0;
 
@@ -89,12 +99,12 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
     double2* As = gsm + (size_t)stage * 2 * GB_TILE_ELEMS;
     double2* Bs = As + GB_TILE_ELEMS;
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; r < GemmGeom<MI>::LOADS; r++) {
       int e = tid + r * GB_THREADS;
-      if (OPA == 0) { int k = e >> 6, m = e & 63; cp_async16(As + k * GB_LD_KM + m, Ag + (size_t)(k0 + k) * D + m0 + m); }
-      else          { int k = e & 7, m = e >> 3;  cp_async16(As + m * GB_LD_MK + k, Ag + (size_t)(m0 + m) * D + k0 + k); }
-      if (OPB == 0) { int k = e & 7, n = e >> 3;  cp_async16(Bs + n * GB_LD_MK + k, Bg + (size_t)(n0 + n) * D + k0 + k); }
-      else          { int k = e >> 6, n = e & 63; cp_async16(Bs + k * GB_LD_KM + n, Bg + (size_t)(k0 + k) * D + n0 + n); }
+      if (OPA == 0) { int k = e / GB_M, m = e % GB_M; cp_async16(As + k * GB_LD_KM + m, Ag + (size_t)(k0 + k) * D + m0 + m); }
+      else          { int k = e & 7, m = e >> 3;      cp_async16(As + m * GB_LD_MK + k, Ag + (size_t)(m0 + m) * D + k0 + k); }
+      if (OPB == 0) { int k = e & 7, n = e >> 3;      cp_async16(Bs + n * GB_LD_MK + k, Bg + (size_t)(n0 + n) * D + k0 + k); }
+      else          { int k = e / GB_N, n = e % GB_N; cp_async16(Bs + k * GB_LD_KM + n, Bg + (size_t)(k0 + k) * D + n0 + n); }
     }
   };
 
@@ -116,22 +126,22 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
     const double2* Bs = As + GB_TILE_ELEMS;
 #pragma unroll
     for (int kk = 0; kk < GB_K; kk += 4) {
-      double2 a[4], bf[2];
+      double2 a[MI], bf[NJ];
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < MI; i++) {
         a[i] = (OPA == 0) ? As[(kk + q) * GB_LD_KM + wm0 + 8 * i + g] : As[(wm0 + 8 * i + g) * GB_LD_MK + kk + q];
         if (OPA == 1) a[i].y = -a[i].y;
       }
 #pragma unroll
-      for (int j = 0; j < 2; j++) {
+      for (int j = 0; j < NJ; j++) {
         bf[j] = (OPB == 0) ? Bs[(wn0 + 8 * j + g) * GB_LD_MK + kk + q] : Bs[(kk + q) * GB_LD_KM + wn0 + 8 * j + g];
         if (OPB == 1) bf[j].y = -bf[j].y;
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+      for (int i = 0; i < MI; i++) {
         const double nai = -a[i].y;
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
+        for (int j = 0; j < NJ; j++) {
           dmma884(acc[i][j][0], acc[i][j][1], a[i].x, bf[j].x);
           dmma884(acc[i][j][2], acc[i][j][3], a[i].x, bf[j].y);
           dmma884(acc[i][j][0], acc[i][j][1], nai, bf[j].y);
@@ -163,9 +173,9 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
       ccoef(eo.aux[x].coef, eo.aux[x].pow2, eo.aux[x].cz, auxr[x], auxi[x]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < MI; i++)
 #pragma unroll
-      for (int j = 0; j < 2; j++)
+      for (int j = 0; j < NJ; j++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int row = m0 + wm0 + 8 * i + g, col = n0 + wn0 + 8 * j + 2 * q + e;

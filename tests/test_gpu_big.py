@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 SYS = {"state": orc.STATE_TRANSFER, "unitary": orc.UNITARY_GATE, "coherence": orc.COHERENCE_TRANSFER}
 
 
-@pytest.mark.parametrize("D,N", [(64, 12), (20, 7), (100, 5), (128, 9), (64, 1), (64, 2), (64, 3)])
+@pytest.mark.parametrize("D,N", [(64, 12), (20, 7), (32, 9), (90, 5), (100, 5), (128, 9), (64, 1), (64, 2), (64, 3)])
 @pytest.mark.parametrize("sys_name", ["state", "unitary", "coherence"])
 def test_first_order_dense_random(D, N, sys_name):
     K, T = 3, 0.8
@@ -71,7 +71,7 @@ def test_propagators_and_total_big():
     assert np.max(np.abs(qoc.pw_evolve(A, B, x, K, dt, N, I) - orc.pw_evolve(A, B, x, dt, I))) < 1e-12
 
 
-@pytest.mark.parametrize("D,N", [(64, 6), (40, 4)])
+@pytest.mark.parametrize("D,N", [(64, 6), (40, 4), (24, 5)])
 @pytest.mark.parametrize("sys_name", ["state", "unitary", "coherence"])
 def test_exact_gradient_big(D, N, sys_name):
     """Exact (ADGRAPE-semantics) gradient on the tiled-GEMM path: Frechet derivative of the Taylor-8 scheme."""
