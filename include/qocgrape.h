@@ -130,6 +130,25 @@ int qoc_comm_export(qoc_handle* h, unsigned char* handle /* [QOC_IPC_HANDLE_BYTE
 int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsigned char* handles);
 int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);
 
+/* ---- the caller of the path: L-BFGS inside the library ---------------------------------------
+ * Replaces `Optim.optimize(Optim.only_fg!(topt), guess, LBFGS(), optim_options)` (src/solve.jl:138, :244) for a
+ * single pulse (R = 1): two-loop recursion with `history` pairs and a backtracking Armijo line search on the host,
+ * every evaluation being one qoc_eval (a CUDA-graph replay).  Stops on ||g||_inf <= g_tol (Optim's default criterion,
+ * 1e-8), on a relative decrease below f_tol, or after max_iters iterations.  x0 / x_out: [N*K] like qoc_eval. */
+typedef struct qoc_lbfgs_options {
+  int max_iters;        /* <= 0: 1000 (Optim.Options default) */
+  int history;          /* <= 0: 10 (Optim.LBFGS default m) */
+  double g_tol;         /* <= 0: 1e-8 */
+  double f_tol;         /* < 0: 0 (disabled, Optim default) */
+  int max_linesearch;   /* <= 0: 30 */
+} qoc_lbfgs_options;
+typedef struct qoc_lbfgs_result {
+  double minimum;       /* res.minimum */
+  double g_norm;        /* ||g||_inf at the minimizer */
+  int iterations, f_calls, converged;
+} qoc_lbfgs_result;
+int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbfgs_options* opt, double* x_out, qoc_lbfgs_result* res);
+
 int qoc_get_stats(qoc_handle* h, qoc_stats* out);
 /* Message of the last error on this handle (or of the last failed qoc_create when h == NULL). */
 const char* qoc_last_error(qoc_handle* h);

@@ -14,7 +14,7 @@ IPC_HANDLE_BYTES = 64
 
 EXPORTS = ["qoc_version", "qoc_create", "qoc_destroy", "qoc_set_system", "qoc_eval", "qoc_eval_device",
            "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error",
-           "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device"]
+           "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device", "qoc_minimize_lbfgs"]
 
 
 class QocDesc(C.Structure):
@@ -27,6 +27,16 @@ class QocStats(C.Structure):
     _fields_ = [("n_evals", C.c_longlong), ("n_launches", C.c_longlong), ("launches_last_eval", C.c_int),
                 ("gpu_ms_last_eval", C.c_float), ("workspace_bytes", C.c_longlong), ("path", C.c_int),
                 ("main_kernel_ms_avg", C.c_float), ("main_kernel_samples", C.c_int)]
+
+
+class QocLbfgsOptions(C.Structure):
+    _fields_ = [("max_iters", C.c_int), ("history", C.c_int), ("g_tol", C.c_double), ("f_tol", C.c_double),
+                ("max_linesearch", C.c_int)]
+
+
+class QocLbfgsResult(C.Structure):
+    _fields_ = [("minimum", C.c_double), ("g_norm", C.c_double), ("iterations", C.c_int), ("f_calls", C.c_int),
+                ("converged", C.c_int)]
 
 
 class QocError(RuntimeError):
@@ -59,6 +69,7 @@ def load():
     lib.qoc_total_propagator.argtypes = [vp, vp, vp]
     lib.qoc_propagators.argtypes = [vp, vp, vp, C.c_int]
     lib.qoc_get_stats.argtypes = [vp, C.POINTER(QocStats)]
+    lib.qoc_minimize_lbfgs.argtypes = [vp, vp, C.POINTER(QocLbfgsOptions), vp, C.POINTER(QocLbfgsResult)]
     lib.qoc_comm_export.argtypes = [vp, vp]
     lib.qoc_comm_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.qoc_eval_allreduce_device.argtypes = [vp, vp, vp, C.c_int, vp]

@@ -742,6 +742,83 @@ extern "C" int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, dou
   return launch_check(h, "oneshot_allreduce_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------ L-BFGS
+extern "C" int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbfgs_options* opt, double* x_out, qoc_lbfgs_result* res) {
+  if (!h) return QOC_EINVAL;
+  if (!x0 || !x_out || !res) { h->err = "qoc_minimize_lbfgs: null pointer"; return QOC_EINVAL; }
+  if (h->d.R != 1) { h->err = "qoc_minimize_lbfgs: the handle must be created with R = 1"; return QOC_EINVAL; }
+  const int n = h->NK;
+  const int max_iters = opt && opt->max_iters > 0 ? opt->max_iters : 1000;
+  const int m = opt && opt->history > 0 ? opt->history : 10;
+  const double g_tol = opt && opt->g_tol > 0 ? opt->g_tol : 1e-8;
+  const double f_tol = opt && opt->f_tol >= 0 ? opt->f_tol : 0.0;
+  const int max_ls = opt && opt->max_linesearch > 0 ? opt->max_linesearch : 30;
+  std::vector<double> x(x0, x0 + n), g(n), xn(n), gn(n), dir(n), alpha(m), rho(m);
+  std::vector<std::vector<double>> S(m, std::vector<double>(n)), Y(m, std::vector<double>(n));
+  auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double s = 0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; };
+  auto ninf = [&](const std::vector<double>& a) { double s = 0; for (int i = 0; i < n; i++) s = std::max(s, std::fabs(a[i])); return s; };
+  double f = 0, fnew = 0;
+  int rc = qoc_eval(h, x.data(), &f, g.data());
+  if (rc != QOC_OK) return rc;
+  int f_calls = 1, stored = 0, head = 0, it = 0, converged = 0;
+  for (; it < max_iters; it++) {
+    if (ninf(g) <= g_tol) { converged = 1; break; }
+    // two-loop recursion: dir = -H g
+    for (int i = 0; i < n; i++) dir[i] = -g[i];
+    for (int j = 0; j < stored; j++) {
+      const int idx = (head - 1 - j + 2 * m) % m;
+      alpha[idx] = rho[idx] * dot(S[idx], dir);
+      for (int i = 0; i < n; i++) dir[i] -= alpha[idx] * Y[idx][i];
+    }
+    if (stored > 0) {
+      const int last = (head - 1 + m) % m;
+      const double gamma = dot(S[last], Y[last]) / dot(Y[last], Y[last]);
+      for (int i = 0; i < n; i++) dir[i] *= gamma;
+    }
+    for (int j = stored - 1; j >= 0; j--) {
+      const int idx = (head - 1 - j + 2 * m) % m;
+      const double beta = rho[idx] * dot(Y[idx], dir);
+      for (int i = 0; i < n; i++) dir[i] += (alpha[idx] - beta) * S[idx][i];
+    }
+    double slope = dot(g, dir);
+    if (!(slope < 0)) { for (int i = 0; i < n; i++) dir[i] = -g[i]; slope = -dot(g, g); stored = 0; }   // not a descent direction: restart
+    // backtracking Armijo line search (first iteration: scale the step to a unit-length move)
+    double step = (stored == 0) ? 1.0 / std::max(1.0, std::sqrt(dot(g, g))) : 1.0;
+    bool ok = false;
+    for (int ls = 0; ls < max_ls; ls++) {
+      for (int i = 0; i < n; i++) xn[i] = x[i] + step * dir[i];
+      if ((rc = qoc_eval(h, xn.data(), &fnew, gn.data())) != QOC_OK) return rc;
+      f_calls++;
+      if (fnew <= f + 1e-4 * step * slope) { ok = true; break; }
+      step *= 0.5;
+    }
+    if (!ok) break;                                  // no acceptable step: stop at the current point
+    // expansion towards the (weak) Wolfe curvature condition: while the slope along dir is still steep, try doubling
+    {
+      std::vector<double> xe(n), ge(n);
+      for (int ex = 0; ex < 6 && dot(gn, dir) < 0.9 * slope; ex++) {
+        const double s2 = 2.0 * step;
+        double fe = 0;
+        for (int i = 0; i < n; i++) xe[i] = x[i] + s2 * dir[i];
+        if ((rc = qoc_eval(h, xe.data(), &fe, ge.data())) != QOC_OK) return rc;
+        f_calls++;
+        if (!(fe <= f + 1e-4 * s2 * slope) || fe >= fnew) break;
+        step = s2; fnew = fe; xn.swap(xe); gn.swap(ge);
+      }
+    }
+    for (int i = 0; i < n; i++) { S[head][i] = xn[i] - x[i]; Y[head][i] = gn[i] - g[i]; }
+    const double sy = dot(S[head], Y[head]);
+    const double fprev = f;
+    x.swap(xn); g.swap(gn); f = fnew;
+    if (sy > 1e-12 * std::sqrt(dot(S[head], S[head]) * dot(Y[head], Y[head]))) { rho[head] = 1.0 / sy; head = (head + 1) % m; stored = std::min(stored + 1, m); }
+    if (f_tol > 0 && std::fabs(fprev - f) <= f_tol * std::fabs(f)) { converged = 1; it++; break; }
+  }
+  if (!converged && ninf(g) <= g_tol) converged = 1;
+  memcpy(x_out, x.data(), sizeof(double) * n);
+  res->minimum = f; res->g_norm = ninf(g); res->iterations = it; res->f_calls = f_calls; res->converged = converged;
+  return QOC_OK;
+}
+
 extern "C" int qoc_get_stats(qoc_handle* h, qoc_stats* out) {
   if (!h || !out) return QOC_EINVAL;
   h->st.workspace_bytes = h->ws_bytes + (h->big ? big_workspace(h->big) : 0);

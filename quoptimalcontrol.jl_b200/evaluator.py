@@ -99,6 +99,16 @@ class GrapeEvaluator:
         """qoc_eval_device + fused one-shot all-reduce: FG receives the sum over all ranks (async on `stream`)."""
         self._check(self._lib.qoc_eval_allreduce_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
 
+    def minimize_lbfgs(self, x0, max_iters=0, history=0, g_tol=0.0, f_tol=-1.0, max_linesearch=0):
+        """L-BFGS inside the library (qoc_minimize_lbfgs): returns (x[K, N], result dict).  Single pulse only."""
+        xb = self._pack_x(x0)
+        out = np.empty_like(xb)
+        opt = _lib.QocLbfgsOptions(max_iters=int(max_iters), history=int(history), g_tol=float(g_tol), f_tol=float(f_tol),
+                                   max_linesearch=int(max_linesearch))
+        res = _lib.QocLbfgsResult()
+        self._check(self._lib.qoc_minimize_lbfgs(self._h, xb.ctypes.data, C.byref(opt), out.ctypes.data, C.byref(res)))
+        return np.ascontiguousarray(np.swapaxes(out, 1, 2)[0]), {f: getattr(res, f) for f, _ in res._fields_}
+
     def total_propagator(self, x):
         """pw_evolve with U0 = I (src/timeevolution.jl:28-39): U[R, M, D, D] (squeezed for R = M = 1)."""
         xb = self._pack_x(x)

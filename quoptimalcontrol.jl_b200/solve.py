@@ -27,6 +27,7 @@ class GPUGRAPE:
     convention: str = "inplace"        # UnitaryGate first-order sign: grad_func! vs grad_func
     device: int = 0
     optim_options: dict = field(default_factory=dict)
+    optimizer: str = "scipy"           # "scipy" (L-BFGS-B, host) | "native" (qoc_minimize_lbfgs inside the library)
 
     @property
     def integrator(self):
@@ -54,6 +55,18 @@ class SolutionResult:                  # src/solve.jl:14-20
 
 
 EnsembleSolutionResult = SolutionResult    # src/solve.jl:23-29 has the same fields
+
+
+class _NativeResult:
+    """Result of qoc_minimize_lbfgs with the same attribute names."""
+    def __init__(self, x, info):
+        self.minimum = float(info["minimum"])
+        self.minimizer = x
+        self.iterations = int(info["iterations"])
+        self.f_calls = self.g_calls = int(info["f_calls"])
+        self.converged = bool(info["converged"])
+        self.g_norm = float(info["g_norm"])
+        self.raw = info
 
 
 class _OptimResult:
@@ -97,5 +110,11 @@ def solve(prob, alg=None):
         wts, guess = None, prob.guess
     with GrapeEvaluator(tuples, first.T, alg.n_slices, first.sys_type, wts=wts, gradient=alg.gradient,
                         convention=alg.convention, device=alg.device) as ev:
-        res = _optimize(ev, guess, alg.optim_options)
+        if getattr(alg, "optimizer", "scipy") == "native":
+            o = alg.optim_options or {}
+            x, info = ev.minimize_lbfgs(guess, max_iters=o.get("maxiter", o.get("iterations", 0)), g_tol=o.get("gtol", o.get("g_tol", 0.0)),
+                                        f_tol=o.get("ftol", o.get("f_tol", -1.0)))
+            res = _NativeResult(x, info)
+        else:
+            res = _optimize(ev, guess, alg.optim_options)
     return SolutionResult(res, res.minimum, res.minimizer, prob, alg)
