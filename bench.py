@@ -297,7 +297,8 @@ def main():
         peak, peak_src = float(pj["fp64_dmma_tflops"]), pj["source"]
     k_ms = st["main_kernel_ms_avg"] or ms
     if st["path"] == 1:
-        kernel_name = "chain_kernel (warp-resident FP64 DMMA), events around each launch"
+        kernel_name = ("warp-resident FP64 DMMA chain kernels (chunk_expm + boundary + sweep, or chain_kernel): %d launches per "
+                       "evaluation incl. the two reduce passes; events around the chain-kernel group" % st["launches_last_eval"])
     else:
         kernel_name = "zgemm_dmma_kernel x %d launches per step (whole step timed: GEMMs are >98%% of it)" % st["launches_last_eval"]
     achieved = flops_rank / (k_ms * 1e-3) / 1e12
@@ -386,7 +387,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["name"], "D": D, "K": K, "N": N, "M": M, "pulses_per_step": evals_per_step,
                        "gradient": cfg["gradient"], "parallelism": parallelism,
-                       "l2": "no flush: each step streams its 2 x %.2f GB propagator/state stores (>> 126 MB L2)" % (st["workspace_bytes"] / 2e9)},
+                       "l2": "no flush: every step writes and re-reads its per-slice propagator (and state) stores, %.2f GB of workspace >> 126 MB L2" % (st["workspace_bytes"] / 1e9)},
             "e2e": e2e, "gpu_launches": int(st["launches_last_eval"]) * args.steps, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     print(json.dumps(line), flush=True)
