@@ -29,11 +29,20 @@ constexpr double BT8_X1 = 0.10836465678522780852, BT8_X2 = 0.0270911641963069521
 // ---------------------------------------------------------------------------------------------- small kernels
 // out_t[e] = f(A[e] + sum_j x[t][j] B_j[e]); mode 0/2: -i*dt*H (generator), mode 1: H.  One thread per element,
 // looping over a range of slices so A and B_j are read once.
-__global__ void big_assemble_kernel(const double2* __restrict__ A, const double2* __restrict__ B, const double* __restrict__ x,
-                                    double2* __restrict__ out, int DD, int K, int N, int slices_per_block, double dt, int mode) {
+// blockIdx.z = chain q of the batch: member[q] selects the system, pulse[q] the pulse; chain q owns the N+1 slots
+// [q*(N+1), (q+1)*(N+1)) of `out` (slot N is zeroed: exp(0) = I keeps the batched launches well defined).
+__global__ void big_assemble_kernel(const double2* __restrict__ A_all, const double2* __restrict__ B_all, const double* __restrict__ x_all,
+                                    double2* __restrict__ out_all, int DD, int K, int N, int slices_per_block, double dt, int mode,
+                                    const int* __restrict__ member, const int* __restrict__ pulse) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= DD) return;
+  const int q = blockIdx.z;
+  const double2* A = A_all + (size_t)member[q] * DD;
+  const double2* B = B_all + (size_t)member[q] * (K > 0 ? K : 1) * DD;
+  const double* x = x_all + (size_t)pulse[q] * N * K;
+  double2* out = out_all + (size_t)q * (N + 1) * DD;
   int t0 = blockIdx.y * slices_per_block, t1 = min(N, t0 + slices_per_block);
+  if (t1 == N) out[(size_t)N * DD + e] = make_double2(0.0, 0.0);
   double2 a = A[e];
   for (int t = t0; t < t1; t++) {
     double hr = a.x, hi = a.y;
@@ -72,9 +81,13 @@ __global__ void big_scale_power_kernel(const float* __restrict__ norms, int N, f
 }
 // tau = sum conj(X) .* Y over D*D elements (one block, fixed-order tree); then the figure of merit.
 //   unitary (reference): X = S_N, Y = Xt, fom = Re(tau^2);   density: X = Xt, Y = S_N, fom = 1 - |tau|^2/D^2
-__global__ void big_fom_kernel(const double2* __restrict__ X, const double2* __restrict__ Y, int DD, int unitary, double invD2,
-                               double* __restrict__ tau_fom /* [3]: tau_re, tau_im, fom */) {
+// blockIdx.x = chain of the batch; X, Y advance by xs, ys elements per chain; tau_fom has 4 doubles per chain.
+__global__ void big_fom_kernel(const double2* __restrict__ X_all, long xs, const double2* __restrict__ Y_all, long ys, int DD, int unitary,
+                               double invD2, double* __restrict__ tau_fom_all /* [chain][4]: tau_re, tau_im, fom, - */) {
   __shared__ double sr[256], si[256];
+  const double2* X = X_all + (size_t)blockIdx.x * xs;
+  const double2* Y = Y_all + (size_t)blockIdx.x * ys;
+  double* tau_fom = tau_fom_all + (size_t)blockIdx.x * 4;
   double pr = 0, pi = 0;
   for (int e = threadIdx.x; e < DD; e += blockDim.x) {
     double2 a = X[e], b = Y[e];
@@ -90,22 +103,25 @@ __global__ void big_fom_kernel(const double2* __restrict__ X, const double2* __r
 }
 // g[t][c] = Re( f * sum_nz B_c[a][b] * W_t[b][a] ), one block per (slice, control) over the control's non-zeros.
 //   f = i*dt (density) or 2*(+-i dt)*tau (unitary, tau read from tau_fom)
+// blockIdx.z = chain q of the batch: W slots q*(N+1)+t, COO lists of the chain's member (coo_off[q]), tau and g per chain.
 struct BigTraceParams {
-  const double2* W; int D, K, N; const int* coo_ptr; const int2* coo_idx; const double2* coo_val;
-  const double* tau_fom; int unitary; double dt; int sign_static; double* g /* [N][K] */; int exact; double invD2;
+  const double2* W; int D, K, N; const int* coo_ptr_all; const int* coo_off; const int2* coo_idx; const double2* coo_val;
+  const double* tau_fom; int unitary; double dt; int sign_static; double* g /* [chain][N][K] */; int exact; double invD2;
 };
 __global__ void big_trace_kernel(const BigTraceParams p) {
   __shared__ double sr[128];
-  int t = blockIdx.x, c = blockIdx.y;
+  int t = blockIdx.x, c = blockIdx.y, q = blockIdx.z;
+  const double* tau_fom = p.tau_fom + (size_t)q * 4;
+  const int* coo_ptr = p.coo_ptr_all + p.coo_off[q];
   double fr, fi;
   if (p.exact) {   // -(2/D^2) (conj(tau)) (-i dt): tau is already folded into Y for the density types
     const double k = 2.0 * p.dt * p.invD2;
-    if (p.unitary) { fr = k * p.tau_fom[1]; fi = k * p.tau_fom[0]; } else { fr = 0.0; fi = k; }
-  } else if (p.unitary) { double sg = 2.0 * p.sign_static * p.dt; fr = -sg * p.tau_fom[1]; fi = sg * p.tau_fom[0]; }
+    if (p.unitary) { fr = k * tau_fom[1]; fi = k * tau_fom[0]; } else { fr = 0.0; fi = k; }
+  } else if (p.unitary) { double sg = 2.0 * p.sign_static * p.dt; fr = -sg * tau_fom[1]; fi = sg * tau_fom[0]; }
   else { fr = 0.0; fi = p.dt; }
-  const double2* W = p.W + (size_t)t * p.D * p.D;
+  const double2* W = p.W + ((size_t)q * (p.N + 1) + t) * p.D * p.D;
   double acc = 0;
-  for (int e = p.coo_ptr[c] + threadIdx.x; e < p.coo_ptr[c + 1]; e += blockDim.x) {
+  for (int e = coo_ptr[c] + threadIdx.x; e < coo_ptr[c + 1]; e += blockDim.x) {
     int2 ab = p.coo_idx[e]; double2 bv = p.coo_val[e];
     double2 w = W[(size_t)ab.x * p.D + ab.y];            // W[b][a] at column a = ab.x, row b = ab.y
     double zr = bv.x * w.x - bv.y * w.y, zi = bv.x * w.y + bv.y * w.x;
@@ -114,23 +130,34 @@ __global__ void big_trace_kernel(const BigTraceParams p) {
   sr[threadIdx.x] = acc;
   __syncthreads();
   for (int o = blockDim.x / 2; o; o >>= 1) { if (threadIdx.x < o) sr[threadIdx.x] += sr[threadIdx.x + o]; __syncthreads(); }
-  if (threadIdx.x == 0) p.g[(size_t)t * p.K + c] = sr[0];
+  if (threadIdx.x == 0) p.g[((size_t)q * p.N + t) * p.K + c] = sr[0];
 }
 // FG[0] += w * fom; FG[1 + i] += w * g[i]   (stream order makes the member sum deterministic: k ascending)
-__global__ void big_accumulate_kernel(double* __restrict__ FG, const double* __restrict__ tau_fom, const double* __restrict__ g,
-                                      const double* __restrict__ wts, int k, int NK, int first, int want_grad) {
+// the nb chains of a batch are folded in ascending order (chain = pulse*M + member), member 0 starts its pulse's row
+__global__ void big_accumulate_kernel(double* __restrict__ FG_all, const double* __restrict__ tau_fom, const double* __restrict__ g,
+                                      const double* __restrict__ wts, const int* __restrict__ member, const int* __restrict__ pulse,
+                                      int nb, int NK, int want_grad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > NK) return;
   if (i > 0 && !want_grad) return;
-  double w = wts[k];
-  double v = i == 0 ? tau_fom[2] : g[i - 1];
-  FG[i] = first ? w * v : FG[i] + w * v;
+  for (int q = 0; q < nb; q++) {
+    double* FG = FG_all + (size_t)pulse[q] * (NK + 1);
+    double w = wts[member[q]];
+    double v = i == 0 ? tau_fom[(size_t)q * 4 + 2] : g[(size_t)q * NK + i - 1];
+    FG[i] = member[q] == 0 ? w * v : FG[i] + w * v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- host state
 struct BigState {
   qoc_desc d{};
   int Dp = 0, BT = 64, Cn = 1, Lmax = 1, unitary = 0;   // BT: CTA tile edge of the GEMM kernel (64, or 32 when that pads D tighter)
+  // Chains (pulse r, member k) are evaluated Bc at a time: chain q of a batch owns slots [q*(N+1), (q+1)*(N+1)) of every
+  // per-slice buffer and chunks [q*Cn, (q+1)*Cn), so all launches simply get a Bc times larger batch dimension.
+  int Bc = 1, tabw = 1;
+  int batch_c0 = -1, batch_nb = 0;                      // batch currently described on the device (reset by set_system)
+  int *chain_member = nullptr, *chain_pulse = nullptr, *chain_coo = nullptr;   // device [Bc]
+  double2 *XiQ = nullptr, *XtQ = nullptr;                                     // per-chain copies of Xi, Xt for the batch
   size_t DD = 0;
   std::vector<int> start, len;
   cudaStream_t sA = nullptr, sB = nullptr;
@@ -166,7 +193,7 @@ static inline long long big_workspace(BigState* s) { return s ? s->ws : 0; }
 
 static inline void big_destroy(BigState* s) {
   if (!s) return;
-  void* ptrs[] = {s->A, s->B, s->Xi, s->Xt, s->Q, s->T, s->tmpF, s->tmpB, s->tab2A, s->tab2T, s->tab0, s->tab4F, s->tab4B,
+  void* ptrs[] = {s->chain_member, s->chain_pulse, s->chain_coo, s->XiQ, s->XtQ, s->A, s->B, s->Xi, s->Xt, s->Q, s->T, s->tmpF, s->tmpB, s->tab2A, s->tab2T, s->tab0, s->tab4F, s->tab4B,
                   s->s_dev, s->norms, s->tau_fom, s->gk, s->coo_ptr, s->coo_idx, s->coo_val};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& b : s->buf) if (b) cudaFree(b);
@@ -206,31 +233,50 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
   BIG_CUDA(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
   BIG_CUDA(cudaEventCreateWithFlags(&s->evB, cudaEventDisableTiming));
   const size_t DD = s->DD;
+  {  // batch size: as many chains as fit in half of the free device memory (exact mode keeps its many intermediates per chain)
+    size_t fre = 0, tot = 0;
+    BIG_CUDA(cudaMemGetInfo(&fre, &tot));
+    const double per_chain = 7.5 * (double)(d.N + 1) * DD * sizeof(double2);
+    long bc = (long)(0.5 * (double)fre / per_chain);
+    bc = std::max(1L, std::min(std::min(bc, 16384L), (long)d.M * d.R));
+    if (s->exact) bc = 1;
+    if (const char* e = getenv("QOC_BIG_BATCH")) bc = std::max(1L, std::min((long)atoi(e), (long)d.M * d.R));
+    s->Bc = (int)bc;
+  }
+  const int Bc = s->Bc;
+  s->tabw = Bc * Cn;
   if ((rc = big_alloc(s, &s->A, (size_t)d.M * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->B, (size_t)d.M * std::max(d.K, 1) * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->Xi, (size_t)d.M * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->Xt, (size_t)d.M * DD, err))) return rc;
-  for (auto& b : s->buf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
+  for (auto& b : s->buf) if ((rc = big_alloc(s, &b, (size_t)Bc * (d.N + 1) * DD, err))) return rc;
   if (s->exact) for (auto& b : s->xbuf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->Q, (size_t)2 * Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->T, (size_t)Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->tmpF, (size_t)Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->tmpB, (size_t)Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Q, (size_t)2 * Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->T, (size_t)Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->tmpF, (size_t)Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->tmpB, (size_t)Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->XiQ, (size_t)Bc * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->XtQ, (size_t)Bc * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->chain_member, (size_t)Bc, err))) return rc;
+  if ((rc = big_alloc(s, &s->chain_pulse, (size_t)Bc, err))) return rc;
+  if ((rc = big_alloc(s, &s->chain_coo, (size_t)Bc, err))) return rc;
   if ((rc = big_alloc(s, &s->s_dev, 1, err))) return rc;
-  if ((rc = big_alloc(s, &s->norms, (size_t)d.N, err))) return rc;
-  if ((rc = big_alloc(s, &s->tau_fom, 4, err))) return rc;
-  if ((rc = big_alloc(s, &s->gk, (size_t)d.N * std::max(d.K, 1), err))) return rc;
-  // lock-step index tables
-  const int L = s->Lmax;
-  std::vector<int> t2A((size_t)L * Cn, -1), t2T((size_t)L * Cn, -1), t0(Cn), t4F((size_t)L * Cn, -1), t4B((size_t)L * Cn, -1);
-  for (int c = 0; c < Cn; c++) {
-    t0[c] = s->start[c];
-    for (int j = 0; j < L; j++) {
-      if (j >= 1 && j < s->len[c]) t2A[(size_t)j * Cn + c] = s->start[c] + j;
-      if (j == s->len[c] - 1) t2T[(size_t)j * Cn + c] = c;
-      if (j < s->len[c] - 1) { t4F[(size_t)j * Cn + c] = s->start[c] + j; t4B[(size_t)j * Cn + c] = s->start[c] + s->len[c] - 1 - j; }
+  if ((rc = big_alloc(s, &s->norms, (size_t)Bc * (d.N + 1), err))) return rc;
+  if ((rc = big_alloc(s, &s->tau_fom, (size_t)Bc * 4, err))) return rc;
+  if ((rc = big_alloc(s, &s->gk, (size_t)Bc * d.N * std::max(d.K, 1), err))) return rc;
+  // lock-step index tables over the virtual chain: row j, column q*Cn + c; entries are virtual slot indices q*(N+1) + t
+  const int L = s->Lmax, W_ = s->tabw, N1 = d.N + 1;
+  std::vector<int> t2A((size_t)L * W_, -1), t2T((size_t)L * W_, -1), t0(W_), t4F((size_t)L * W_, -1), t4B((size_t)L * W_, -1);
+  for (int q = 0; q < Bc; q++)
+    for (int c = 0; c < Cn; c++) {
+      const int col = q * Cn + c, base = q * N1;
+      t0[col] = base + s->start[c];
+      for (int j = 0; j < L; j++) {
+        if (j >= 1 && j < s->len[c]) t2A[(size_t)j * W_ + col] = base + s->start[c] + j;
+        if (j == s->len[c] - 1) t2T[(size_t)j * W_ + col] = col;
+        if (j < s->len[c] - 1) { t4F[(size_t)j * W_ + col] = base + s->start[c] + j; t4B[(size_t)j * W_ + col] = base + s->start[c] + s->len[c] - 1 - j; }
+      }
     }
-  }
   auto up = [&](int** dst, const std::vector<int>& v) -> int {
     int r = big_alloc(s, dst, v.size(), err); if (r) return r;
     BIG_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -256,6 +302,7 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
   const int M = d.M, K = d.K, D = d.D;
   const size_t dd = (size_t)D * D;
   int rc;
+  s->batch_c0 = -1;
   auto rep = [&](double2* dst, const double* src, size_t per_member, bool sh) -> int {
     for (int k = 0; k < M; k++)
       if ((rc = big_upload_padded(s, dst + (size_t)k * per_member * s->DD, src + (sh ? 0 : (size_t)k * per_member * 2 * dd), per_member, err))) return rc;
@@ -332,7 +379,8 @@ static int big_gemm(BigState* s, int opA, int opB, GemmParams& p, cudaStream_t s
     s->attr_set = true;
   }
   p.D = s->Dp;
-  dim3 grid((s->Dp / s->BT) * (s->Dp / s->BT), p.batch);
+  const int by = std::min(p.batch, 32768);
+  dim3 grid((s->Dp / s->BT) * (s->Dp / s->BT), by, (p.batch + by - 1) / by);
   fn<<<grid, GB_THREADS, smem, st>>>(p);
   BIG_CUDA(cudaGetLastError());
   stats.n_launches++; stats.launches_last_eval++;
@@ -340,22 +388,40 @@ static int big_gemm(BigState* s, int opA, int opB, GemmParams& p, cudaStream_t s
 }
 #define BIG_COUNT() do { BIG_CUDA(cudaGetLastError()); stats.n_launches++; stats.launches_last_eval++; } while (0)
 
-// phase 1: propagators of member k for pulse x (device pointer to [N][K]) into buf[5] (P); returns via s_host
-static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaStream_t st, std::string& err, qoc_stats& stats) {
+// Describe the batch [c0, c0 + nb) of chains (chain = pulse * M + member) to the device and gather their Xi, Xt.
+static int big_set_batch(BigState* s, int c0, int nb, cudaStream_t st, std::string& err) {
+  const int M = s->d.M;
+  if (c0 == s->batch_c0 && nb == s->batch_nb) return QOC_OK;
+  std::vector<int> mem(nb), pul(nb), coo(nb);
+  for (int q = 0; q < nb; q++) { mem[q] = (c0 + q) % M; pul[q] = (c0 + q) / M; coo[q] = (int)s->coo_member_off[mem[q]]; }
+  BIG_CUDA(cudaMemcpyAsync(s->chain_member, mem.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(s->chain_pulse, pul.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(s->chain_coo, coo.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+  for (int q = 0; q < nb; q++) {
+    BIG_CUDA(cudaMemcpyAsync(s->XiQ + (size_t)q * s->DD, s->Xi + (size_t)mem[q] * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    BIG_CUDA(cudaMemcpyAsync(s->XtQ + (size_t)q * s->DD, s->Xt + (size_t)mem[q] * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  }
+  BIG_CUDA(cudaStreamSynchronize(st));     // the host vectors above go out of scope
+  s->batch_c0 = c0; s->batch_nb = nb;
+  return QOC_OK;
+}
+
+// phase 1: propagators of the nb chains of the current batch (x_all: [R][N][K] on the device) into s->Pfinal
+static int big_propagators_phase(BigState* s, int nb, const double* x_all, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   const size_t DD = s->DD; const long sd = (long)DD;
-  const int N = d.N;
+  const int N = d.N, VB = nb * (N + 1);                   // batch over all virtual slots (slot N of every chain holds G = 0)
   double2 *G = s->buf[0], *G2 = s->buf[1], *Y1 = s->buf[2], *L8 = s->buf[3], *R8 = s->buf[4], *P = s->buf[5], *P2 = s->buf[6];
-  dim3 ga((unsigned)((DD + 255) / 256), (N + 63) / 64);
-  big_assemble_kernel<<<ga, 256, 0, st>>>(s->A + (size_t)k * DD, s->B + (size_t)k * std::max(d.K, 1) * DD, x_dev, G, (int)DD, d.K, N, 64, d.T / N, 0);
+  dim3 ga((unsigned)((DD + 255) / 256), (N + 63) / 64, nb);
+  big_assemble_kernel<<<ga, 256, 0, st>>>(s->A, s->B, x_all, G, (int)DD, d.K, N, 64, d.T / N, 0, s->chain_member, s->chain_pulse);
   BIG_COUNT();
-  big_norm_kernel<<<N, 256, 0, st>>>(G, s->Dp, s->norms);
+  big_norm_kernel<<<VB, 256, 0, st>>>(G, s->Dp, s->norms);
   BIG_COUNT();
-  big_scale_power_kernel<<<1, 256, 0, st>>>(s->norms, N, (float)(d.expm_theta > 0 ? d.expm_theta : 0.0694), s->s_dev);
+  big_scale_power_kernel<<<1, 256, 0, st>>>(s->norms, VB, (float)(d.expm_theta > 0 ? d.expm_theta : 0.0694), s->s_dev);
   BIG_COUNT();
   int rc;
   GemmParams p{};
-  p.batch = N; p.s_ptr = s->s_dev;
+  p.batch = VB; p.s_ptr = s->s_dev;
   // G2 = (G/2^s)^2 ; Y1 = x1 G/2^s + x2 G2
   p.A = bmat(G, sd); p.B = bmat(G, sd); p.nout = 2;
   p.out[0] = eout(bmat(G2, sd), 1.0, 2);
@@ -370,23 +436,23 @@ static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaSt
   p.A = bmat(L8, sd); p.B = bmat(R8, sd); p.nout = 1;
   p.out[0] = eout(bmat(P, sd), 1.0, 0, 1.0); eaux(p.out[0], bmat(G, sd), 1.0, 1); eaux(p.out[0], bmat(G2, sd), BT8_Y2);
   if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-  // squarings: the count lives on the device; one small synchronising read per evaluation
+  // squarings: the count lives on the device; one small synchronising read per batch
   int s_host = 0;
   BIG_CUDA(cudaMemcpyAsync(&s_host, s->s_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   BIG_CUDA(cudaStreamSynchronize(st));
   s->s_last = s_host;
-  if (s->exact) {   // keep every intermediate square for the Frechet chain rule: P_0 = buf[5], P_1 = xbuf[11], P_2 = xbuf[12]
+  if (s->exact) {   // keep every intermediate square for the Frechet chain rule (Bc = 1 in exact mode)
     if (s_host > 12) { err = "exact gradient for D > 16 supports at most 12 squarings (||dt*H||_1 <= 284): use more slices"; return QOC_EUNSUPPORTED; }
-    while ((int)s->pchain.size() < s_host) {      // intermediate squares are needed by the chain rule; allocated on first use
-      double2* nb = nullptr;
-      if ((rc = big_alloc(s, &nb, (size_t)(N + 1) * DD, err))) return rc;
-      s->pchain.push_back(nb);
+    while ((int)s->pchain.size() < s_host) {      // allocated on first use
+      double2* nbuf = nullptr;
+      if ((rc = big_alloc(s, &nbuf, (size_t)(N + 1) * DD, err))) return rc;
+      s->pchain.push_back(nbuf);
     }
     std::vector<double2*> chain(1, s->buf[5]);
     chain.insert(chain.end(), s->pchain.begin(), s->pchain.end());
     for (int j = 0; j < s_host; j++) {
       GemmParams q{};
-      q.batch = N; q.A = bmat(chain[j], sd); q.B = bmat(chain[j], sd); q.nout = 1; q.out[0] = eout(bmat(chain[j + 1], sd));
+      q.batch = VB; q.A = bmat(chain[j], sd); q.B = bmat(chain[j], sd); q.nout = 1; q.out[0] = eout(bmat(chain[j + 1], sd));
       if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
     }
     s->Pfinal = chain[s_host];
@@ -394,7 +460,7 @@ static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaSt
   }
   for (int j = 0; j < s_host; j++) {
     GemmParams q{};
-    q.batch = N; q.A = bmat(P, sd); q.B = bmat(P, sd); q.nout = 1; q.out[0] = eout(bmat(P2, sd));
+    q.batch = VB; q.A = bmat(P, sd); q.B = bmat(P, sd); q.nout = 1; q.out[0] = eout(bmat(P2, sd));
     if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
     std::swap(P, P2);
   }
@@ -403,21 +469,24 @@ static int big_propagators_phase(BigState* s, int k, const double* x_dev, cudaSt
   return QOC_OK;
 }
 
-// phase 2: chunk totals T_c (batch Cn, Lmax-1 lock steps)
-static int big_chunk_totals(BigState* s, cudaStream_t st, std::string& err, qoc_stats& stats) {
-  const long sd = (long)s->DD; const int Cn = s->Cn;
+// phase 2: chunk totals T[q*Cn + c] (batch nb*Cn, Lmax-1 lock steps)
+static int big_chunk_totals(BigState* s, int nb, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const long sd = (long)s->DD; const int Cn = s->Cn, N1 = s->d.N + 1;
+  const size_t half = (size_t)s->Bc * Cn * s->DD;
   double2* P = s->Pfinal;
   int rc;
-  for (int c = 0; c < Cn; c++)
-    if (s->len[c] == 1) BIG_CUDA(cudaMemcpyAsync(s->T + (size_t)c * s->DD, P + (size_t)s->start[c] * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  for (int q = 0; q < nb; q++)
+    for (int c = 0; c < Cn; c++)
+      if (s->len[c] == 1)
+        BIG_CUDA(cudaMemcpyAsync(s->T + (size_t)(q * Cn + c) * s->DD, P + (size_t)(q * N1 + s->start[c]) * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
   for (int j = 1; j < s->Lmax; j++) {
     GemmParams p{};
-    p.batch = Cn;
-    p.A = bmat(P, sd, s->tab2A + (size_t)j * Cn);
-    p.B = j == 1 ? bmat(P, sd, s->tab0) : bmat(s->Q + (size_t)((j - 1) & 1) * Cn * s->DD, sd);
+    p.batch = nb * Cn;
+    p.A = bmat(P, sd, s->tab2A + (size_t)j * s->tabw);
+    p.B = j == 1 ? bmat(P, sd, s->tab0) : bmat(s->Q + (size_t)((j - 1) & 1) * half, sd);
     p.nout = 2;
-    p.out[0] = eout(bmat(s->Q + (size_t)(j & 1) * Cn * s->DD, sd));
-    p.out[1] = eout(bmat(s->T, sd, s->tab2T + (size_t)j * Cn));
+    p.out[0] = eout(bmat(s->Q + (size_t)(j & 1) * half, sd));
+    p.out[1] = eout(bmat(s->T, sd, s->tab2T + (size_t)j * s->tabw));
     if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
   }
   return QOC_OK;
@@ -427,54 +496,55 @@ static int big_chunk_totals(BigState* s, cudaStream_t st, std::string& err, qoc_
 //   W_t = S_t C_t' (- C_t' S_t) = U_t W_0 U_t',   W_0 = Xi C_0' (- C_0' Xi),   C_0 = U_N' Xt (U_N).
 // One forward conjugation recursion W_{t+1} = P_t W_t P_t' replaces the separate state and costate sweeps and the
 // per-slice W products: 7 GEMMs per slice instead of 11.  Same figure of merit and gradient to rounding.
-static int big_eval_member_unitary(BigState* s, int k, cudaStream_t st, std::string& err, qoc_stats& stats) {
+// All nb chains of the batch advance together (batch dimension nb, nb*Cn or nb*(N+1)).
+static int big_eval_batch_unitary(BigState* s, int nb, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   const size_t DD = s->DD; const long sd = (long)DD;
   const int N = d.N, Cn = s->Cn, U = s->unitary;
+  const long cs = (long)(N + 1) * (long)DD;          // chain stride in the per-slice buffers
+  const long ts = (long)Cn * (long)DD;               // chain stride in the chunk-total buffer
+  const size_t half = (size_t)s->Bc * Cn * DD;
   int rc;
   double2 *P = s->Pfinal, *W = s->buf[3];
-  const double2* Xi = s->Xi + (size_t)k * DD;
-  const double2* Xt = s->Xt + (size_t)k * DD;
-  GemmParams p{}; p.batch = 1; p.nout = 1;
-  // U_N = T_{Cn-1} ... T_0
-  const double2* Un = s->T;
+  GemmParams p{}; p.batch = nb; p.nout = 1;
+  // U_N = T_{Cn-1} ... T_0 per chain
+  const double2* Un = s->T; long us = ts;
   for (int c = 1; c < Cn; c++) {
-    double2* dst = s->Q + (size_t)(c & 1) * Cn * DD;
-    p.A = bmat(s->T + (size_t)c * DD, 0); p.B = bmat(Un, 0); p.out[0] = eout(bmat(dst, 0));
+    double2* dst = s->Q + (size_t)(c & 1) * half;
+    p.A = bmat(s->T + (size_t)c * DD, ts); p.B = bmat(Un, us); p.out[0] = eout(bmat(dst, sd));
     if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-    Un = dst;
+    Un = dst; us = sd;
   }
   // C_0 = U_N' Xt (U_N)
   double2* C0 = s->tmpB;
-  if (U) { p.A = bmat(Un, 0); p.B = bmat(Xt, 0); p.out[0] = eout(bmat(C0, 0)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc; }
+  if (U) { p.A = bmat(Un, us); p.B = bmat(s->XtQ, sd); p.out[0] = eout(bmat(C0, sd)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc; }
   else {
-    p.A = bmat(Xt, 0); p.B = bmat(Un, 0); p.out[0] = eout(bmat(s->tmpF, 0)); if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-    p.A = bmat(Un, 0); p.B = bmat(s->tmpF, 0); p.out[0] = eout(bmat(C0, 0)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
+    p.A = bmat(s->XtQ, sd); p.B = bmat(Un, us); p.out[0] = eout(bmat(s->tmpF, sd)); if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+    p.A = bmat(Un, us); p.B = bmat(s->tmpF, sd); p.out[0] = eout(bmat(C0, sd)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
   }
   // figure of merit: unitary tau = tr(S_N' Xt) = tr(Xi' C_0); density tau = tr(Xt' S_N) = tr(C_0' Xi)
   const double invD2 = 1.0 / ((double)d.D * d.D);
-  if (U) big_fom_kernel<<<1, 256, 0, st>>>(Xi, C0, (int)DD, 1, invD2, s->tau_fom);
-  else big_fom_kernel<<<1, 256, 0, st>>>(C0, Xi, (int)DD, 0, invD2, s->tau_fom);
+  if (U) big_fom_kernel<<<nb, 256, 0, st>>>(s->XiQ, sd, C0, sd, (int)DD, 1, invD2, s->tau_fom);
+  else big_fom_kernel<<<nb, 256, 0, st>>>(C0, sd, s->XiQ, sd, (int)DD, 0, invD2, s->tau_fom);
   BIG_COUNT();
-  // W_0 = Xi C_0' (- C_0' Xi)
-  p.A = bmat(Xi, 0); p.B = bmat(C0, 0); p.out[0] = eout(bmat(W, 0)); if ((rc = big_gemm(s, 0, 1, p, st, err, stats))) return rc;
+  // W_0 = Xi C_0' (- C_0' Xi) into slot 0 of every chain
+  p.A = bmat(s->XiQ, sd); p.B = bmat(C0, sd); p.out[0] = eout(bmat(W, cs)); if ((rc = big_gemm(s, 0, 1, p, st, err, stats))) return rc;
   if (!U) {
-    p.A = bmat(C0, 0); p.B = bmat(Xi, 0); p.out[0] = eout(bmat(W, 0), -1.0); eaux(p.out[0], bmat(W, 0), 1.0);
+    p.A = bmat(C0, sd); p.B = bmat(s->XiQ, sd); p.out[0] = eout(bmat(W, cs), -1.0); eaux(p.out[0], bmat(W, cs), 1.0);
     if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
   }
   // chunk-boundary operators W[start_{c+1}] = T_c W[start_c] T_c'
   for (int c = 0; c + 1 < Cn; c++) {
-    const double2* Tc = s->T + (size_t)c * DD;
-    double2* Win = W + (size_t)s->start[c] * DD;
-    double2* Wout = W + (size_t)(s->start[c] + s->len[c]) * DD;
-    GemmParams q{}; q.batch = 1; q.nout = 1;
-    q.A = bmat(Win, 0); q.B = bmat(Tc, 0); q.out[0] = eout(bmat(s->tmpF, 0)); if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
-    q.A = bmat(Tc, 0); q.B = bmat(s->tmpF, 0); q.out[0] = eout(bmat(Wout, 0)); if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+    GemmParams q{}; q.batch = nb; q.nout = 1;
+    q.A = bmat(W + (size_t)s->start[c] * DD, cs); q.B = bmat(s->T + (size_t)c * DD, ts); q.out[0] = eout(bmat(s->tmpF, sd));
+    if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
+    q.A = bmat(s->T + (size_t)c * DD, ts); q.B = bmat(s->tmpF, sd); q.out[0] = eout(bmat(W + (size_t)(s->start[c] + s->len[c]) * DD, cs));
+    if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
   }
-  // lock-step conjugation sweeps inside all chunks: W[t+1] = P_t W[t] P_t'
+  // lock-step conjugation sweeps inside all chunks of all chains: W[t+1] = P_t W[t] P_t'
   for (int j = 0; j < s->Lmax - 1; j++) {
-    const int* tF = s->tab4F + (size_t)j * Cn;
-    GemmParams q{}; q.batch = Cn; q.nout = 1;
+    const int* tF = s->tab4F + (size_t)j * s->tabw;
+    GemmParams q{}; q.batch = nb * Cn; q.nout = 1;
     q.A = bmat(W, sd, tF); q.B = bmat(P, sd, tF); q.out[0] = eout(bmat(s->tmpF, sd));
     if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
     q.A = bmat(P, sd, tF); q.B = bmat(s->tmpF, sd); q.out[0] = eout(bmat(W, sd, tF, 1));
@@ -482,26 +552,25 @@ static int big_eval_member_unitary(BigState* s, int k, cudaStream_t st, std::str
   }
   if (d.K > 0) {
     BigTraceParams tp;
-    tp.W = W; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
+    tp.W = W; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr_all = s->coo_ptr; tp.coo_off = s->chain_coo; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
     tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.g = s->gk; tp.exact = 0; tp.invD2 = 0.0;
-    big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
+    big_trace_kernel<<<dim3(N, d.K, nb), 128, 0, st>>>(tp);
     BIG_COUNT();
   }
   return QOC_OK;
 }
 
-static int big_eval_member(BigState* s, int k, const double* x_dev, int want_grad, cudaStream_t st, std::string& err, qoc_stats& stats) {
+// General path (Liouvillians, exact gradient, value-only): ONE chain, in slot 0 of the batch buffers.
+static int big_eval_member(BigState* s, int want_grad, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   const size_t DD = s->DD; const long sd = (long)DD;
   const int N = d.N, Cn = s->Cn, U = s->unitary;
+  const size_t tw = (size_t)s->tabw;
   int rc;
-  if ((rc = big_propagators_phase(s, k, x_dev, st, err, stats))) return rc;
   double2 *P = s->Pfinal, *S = s->exact ? s->xbuf[0] : s->buf[1], *C = s->exact ? s->xbuf[1] : s->buf[2], *W = s->buf[3];
-  if ((rc = big_chunk_totals(s, st, err, stats))) return rc;
-  if (s->herm && !s->exact && want_grad) return big_eval_member_unitary(s, k, st, err, stats);
   // ---- phase 3: boundary states (stream sA) and boundary costates (stream sB), short sequential chains ----
-  BIG_CUDA(cudaMemcpyAsync(S, s->Xi + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
-  BIG_CUDA(cudaMemcpyAsync(C + (size_t)N * DD, s->Xt + (size_t)k * DD, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(S, s->XiQ, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(C + (size_t)N * DD, s->XtQ, DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
   BIG_CUDA(cudaEventRecord(s->evFork, st));
   BIG_CUDA(cudaStreamWaitEvent(s->sA, s->evFork, 0));
   BIG_CUDA(cudaStreamWaitEvent(s->sB, s->evFork, 0));
@@ -530,8 +599,8 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
     }
     // ---- phase 4: lock-step sweeps inside the chunks, forward on sA, backward on sB ----
     for (int j = 0; j < s->Lmax - 1; j++) {
-      const int* tF = s->tab4F + (size_t)j * Cn;
-      const int* tB = s->tab4B + (size_t)j * Cn;
+      const int* tF = s->tab4F + (size_t)j * tw;
+      const int* tB = s->tab4B + (size_t)j * tw;
       GemmParams p{}; p.batch = Cn; p.nout = 1;
       if (U) {
         p.A = bmat(P, sd, tF); p.B = bmat(S, sd, tF); p.out[0] = eout(bmat(S, sd, tF, 1));                   // S[t+1] = P_t S_t
@@ -556,10 +625,13 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
   BIG_CUDA(cudaStreamWaitEvent(st, s->evB, 0));
   // ---- figure of merit from S[N] and Xt ----
   const double invD2 = 1.0 / ((double)d.D * d.D);
-  if (U && !s->exact) big_fom_kernel<<<1, 256, 0, st>>>(S + (size_t)N * DD, s->Xt + (size_t)k * DD, (int)DD, 1, invD2, s->tau_fom);
-  else big_fom_kernel<<<1, 256, 0, st>>>(s->Xt + (size_t)k * DD, S + (size_t)N * DD, (int)DD, 0, invD2, s->tau_fom);
+  if (U && !s->exact) big_fom_kernel<<<1, 256, 0, st>>>(S + (size_t)N * DD, 0, s->XtQ, 0, (int)DD, 1, invD2, s->tau_fom);
+  else big_fom_kernel<<<1, 256, 0, st>>>(s->XtQ, 0, S + (size_t)N * DD, 0, (int)DD, 0, invD2, s->tau_fom);
   BIG_COUNT();
   if (!want_grad) return QOC_OK;
+  BigTraceParams tp;
+  tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr_all = s->coo_ptr; tp.coo_off = s->chain_coo; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
+  tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.g = s->gk;
   if (s->exact) {
     // ---- exact gradient: Y_t, Frechet derivative Lam_t = L(G_t, Y_t), trace-dots over Lam_t ----
     double2 *G = s->buf[0], *G2 = s->buf[1], *Y1 = s->buf[2], *L8 = s->buf[3], *R8 = s->buf[4];
@@ -607,10 +679,8 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
       std::swap(dP, dPb);
     }
     if (d.K > 0) {
-      BigTraceParams tp;
-      tp.W = dP; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
-      tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = 1; tp.g = s->gk; tp.exact = 1; tp.invD2 = invD2;
-      big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
+      tp.W = dP; tp.sign_static = 1; tp.exact = 1; tp.invD2 = invD2;
+      big_trace_kernel<<<dim3(N, d.K, 1), 128, 0, st>>>(tp);
       BIG_COUNT();
     }
     return QOC_OK;
@@ -626,10 +696,8 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
     }
   }
   if (d.K > 0) {
-    BigTraceParams tp;
-    tp.W = W; tp.D = s->Dp; tp.K = d.K; tp.N = N; tp.coo_ptr = s->coo_ptr + s->coo_member_off[k]; tp.coo_idx = s->coo_idx; tp.coo_val = s->coo_val;
-    tp.tau_fom = s->tau_fom; tp.unitary = U; tp.dt = d.T / N; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.g = s->gk; tp.exact = 0; tp.invD2 = 0.0;
-    big_trace_kernel<<<dim3(N, d.K), 128, 0, st>>>(tp);
+    tp.W = W; tp.sign_static = d.convention == QOC_REF_STATIC ? -1 : 1; tp.exact = 0; tp.invD2 = 0.0;
+    big_trace_kernel<<<dim3(N, d.K, 1), 128, 0, st>>>(tp);
     BIG_COUNT();
   }
   return QOC_OK;
@@ -638,14 +706,20 @@ static int big_eval_member(BigState* s, int k, const double* x_dev, int want_gra
 static inline int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
                            std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
-  const int NK = d.N * d.K;
+  const int NK = d.N * d.K, total = d.M * d.R;
+  const bool batched = s->herm && !s->exact && want_grad;     // closed-system recursion: Bc chains per pass
+  const int step = batched ? s->Bc : 1;
   int rc;
-  for (int r = 0; r < d.R; r++)
-    for (int k = 0; k < d.M; k++) {
-      if ((rc = big_eval_member(s, k, x_dev + (size_t)r * NK, want_grad, st, err, stats))) return rc;
-      big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev + (size_t)r * (NK + 1), s->tau_fom, s->gk, wts_dev, k, NK, k == 0, want_grad);
-      BIG_COUNT();
-    }
+  for (int c0 = 0; c0 < total; c0 += step) {
+    const int nb = std::min(step, total - c0);
+    if ((rc = big_set_batch(s, c0, nb, st, err))) return rc;
+    if ((rc = big_propagators_phase(s, nb, x_dev, st, err, stats))) return rc;
+    if ((rc = big_chunk_totals(s, nb, st, err, stats))) return rc;
+    if (batched) { if ((rc = big_eval_batch_unitary(s, nb, st, err, stats))) return rc; }
+    else if ((rc = big_eval_member(s, want_grad, st, err, stats))) return rc;
+    big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev, s->tau_fom, s->gk, wts_dev, s->chain_member, s->chain_pulse, nb, NK, want_grad);
+    BIG_COUNT();
+  }
   return QOC_OK;
 }
 
@@ -661,43 +735,41 @@ static int big_unpad(BigState* s, double2* dst, const double2* src, size_t count
 
 static inline int big_propagators(BigState* s, const double* x_dev, double2* out, int mode, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
-  const int NK = d.N * d.K;
   int rc;
-  for (int r = 0; r < d.R; r++)
-    for (int k = 0; k < d.M; k++) {
-      const double2* src;
-      if (mode == 0) { if ((rc = big_propagators_phase(s, k, x_dev + (size_t)r * NK, st, err, stats))) return rc; src = s->Pfinal; }
-      else {
-        dim3 ga((unsigned)((s->DD + 255) / 256), (d.N + 63) / 64);
-        big_assemble_kernel<<<ga, 256, 0, st>>>(s->A + (size_t)k * s->DD, s->B + (size_t)k * std::max(d.K, 1) * s->DD, x_dev + (size_t)r * NK,
-                                                s->buf[0], (int)s->DD, d.K, d.N, 64, d.T / d.N, mode);
-        BIG_COUNT();
-        src = s->buf[0];
-      }
-      if ((rc = big_unpad(s, out + ((size_t)r * d.M + k) * d.N * d.D * d.D, src, d.N, st, err))) return rc;
+  for (int c = 0; c < d.M * d.R; c++) {
+    if ((rc = big_set_batch(s, c, 1, st, err))) return rc;
+    const double2* src;
+    if (mode == 0) { if ((rc = big_propagators_phase(s, 1, x_dev, st, err, stats))) return rc; src = s->Pfinal; }
+    else {
+      dim3 ga((unsigned)((s->DD + 255) / 256), (d.N + 63) / 64, 1);
+      big_assemble_kernel<<<ga, 256, 0, st>>>(s->A, s->B, x_dev, s->buf[0], (int)s->DD, d.K, d.N, 64, d.T / d.N, mode, s->chain_member, s->chain_pulse);
+      BIG_COUNT();
+      src = s->buf[0];
     }
+    if ((rc = big_unpad(s, out + (size_t)c * d.N * d.D * d.D, src, d.N, st, err))) return rc;
+  }
   return QOC_OK;
 }
 
 static inline int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
-  const int NK = d.N * d.K;
   const size_t DD = s->DD;
+  const size_t half = (size_t)s->Bc * s->Cn * DD;
   int rc;
-  for (int r = 0; r < d.R; r++)
-    for (int k = 0; k < d.M; k++) {
-      if ((rc = big_propagators_phase(s, k, x_dev + (size_t)r * NK, st, err, stats))) return rc;
-      if ((rc = big_chunk_totals(s, st, err, stats))) return rc;
-      const double2* cur = s->T;                       // U = T_{Cn-1} ... T_0
-      for (int c = 1; c < s->Cn; c++) {
-        double2* dst = s->Q + (size_t)(c & 1) * s->Cn * DD;
-        GemmParams p{}; p.batch = 1; p.nout = 1;
-        p.A = bmat(s->T + (size_t)c * DD, 0); p.B = bmat(cur, 0); p.out[0] = eout(bmat(dst, 0));
-        if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-        cur = dst;
-      }
-      if ((rc = big_unpad(s, out + ((size_t)r * d.M + k) * d.D * d.D, cur, 1, st, err))) return rc;
+  for (int c = 0; c < d.M * d.R; c++) {
+    if ((rc = big_set_batch(s, c, 1, st, err))) return rc;
+    if ((rc = big_propagators_phase(s, 1, x_dev, st, err, stats))) return rc;
+    if ((rc = big_chunk_totals(s, 1, st, err, stats))) return rc;
+    const double2* cur = s->T;                       // U = T_{Cn-1} ... T_0
+    for (int j = 1; j < s->Cn; j++) {
+      double2* dst = s->Q + (size_t)(j & 1) * half;
+      GemmParams p{}; p.batch = 1; p.nout = 1;
+      p.A = bmat(s->T + (size_t)j * DD, 0); p.B = bmat(cur, 0); p.out[0] = eout(bmat(dst, 0));
+      if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+      cur = dst;
     }
+    if ((rc = big_unpad(s, out + (size_t)c * d.D * d.D, cur, 1, st, err))) return rc;
+  }
   return QOC_OK;
 }
 

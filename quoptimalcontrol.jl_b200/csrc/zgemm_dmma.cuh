@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmPar
   constexpr int NJ = MI / 2;
   constexpr int GB_M = GemmGeom<MI>::BT, GB_N = GemmGeom<MI>::BT, GB_LD_KM = GemmGeom<MI>::LD_KM;
   constexpr int GB_TILE_ELEMS = GemmGeom<MI>::TILE_ELEMS;
-  const int b = blockIdx.y;
+  const int b = blockIdx.z * gridDim.y + blockIdx.y;     // batches beyond 65535 spill into grid.z
+  if (b >= p.batch) return;
   bool idle = false;
   const double2* Ag = bm_ptr(p.A, b, idle);
   const double2* Bg = bm_ptr(p.B, b, idle);

@@ -37,6 +37,29 @@ def test_static_sign_and_ensemble():
     assert_parity(F, G, Fo, Go)
 
 
+@pytest.mark.parametrize("batch", [None, 1, 4])
+@pytest.mark.parametrize("sys_name", ["state", "unitary"])
+@pytest.mark.parametrize("D,N", [(32, 11), (20, 7), (64, 5)])
+def test_chain_batching(monkeypatch, batch, sys_name, D, N):
+    """Closed-system chains (members x pulses) ride in the GEMM batch dimension, QOC_BIG_BATCH at a time: an
+    M = 3, R = 2 ensemble evaluated in batches of 6 (default), 1 and 4 + 2 (ragged last batch) agrees with the oracle."""
+    if batch is None:
+        monkeypatch.delenv("QOC_BIG_BATCH", raising=False)
+    else:
+        monkeypatch.setenv("QOC_BIG_BATCH", str(batch))
+    K, T, M, R = 2, 0.7, 3, 2
+    members = [random_system(D, K, seed=900 + 7 * k + D, unitary_targets=(sys_name == "unitary")) for k in range(M)]
+    wts = [0.5, 0.2, 0.3]
+    xs = np.random.default_rng(N + D).uniform(-1, 1, (R, K, N))
+    with qoc.GrapeEvaluator(members, T, N, SYS[sys_name], wts=wts, n_pulses=R) as ev:
+        F, G = ev.eval(xs)
+        F2, G2 = ev.eval(xs)          # cached batch descriptor on the second call
+    for r in range(R):
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, xs[r], T, SYS[sys_name])
+        assert_parity(F[r], G[r], Fo, Go)
+        assert_parity(F2[r], G2[r], Fo, Go)
+
+
 def test_large_norm_squarings():
     D, K, N, T = 64, 2, 4, 2.0
     A, B, Xi, Xt = random_system(D, K, seed=9, scale=6.0)
