@@ -46,6 +46,10 @@ extern "C" {
 #define QOC_REF_INPLACE 0
 #define QOC_REF_STATIC 1
 
+/* qoc_desc.flags */
+#define QOC_FLAG_NO_PURE_STATE 1 /* D > 16 StateTransfer between pure states on a sparse closed system is evaluated with
+                                    state vectors (same F, G to rounding, O(nnz) per slice); set to force the dense path */
+
 /* shared_flags for qoc_set_system: the argument holds ONE matrix (set) used by all M members */
 #define QOC_SHARED_A 1
 #define QOC_SHARED_B 2
@@ -67,7 +71,7 @@ typedef struct qoc_desc {
   int device;        /* CUDA device ordinal */
   double expm_theta; /* scaling threshold of the degree-8 Taylor exponential; <= 0 selects the default
                         (0.0694: truncation error below 2^-53) */
-  int flags;         /* reserved, 0 */
+  int flags;         /* QOC_FLAG_* bits, 0 = defaults */
 } qoc_desc;
 
 typedef struct qoc_stats {
@@ -76,7 +80,8 @@ typedef struct qoc_stats {
   int launches_last_eval;     /* kernels launched by the most recent evaluation */
   float gpu_ms_last_eval;     /* device time of the most recent qoc_eval (CUDA events), 0 for eval_device */
   long long workspace_bytes;  /* device memory held */
-  int path;                   /* 1 = warp-resident DMMA (D <= 16), 2 = tiled DMMA GEMM (D > 16) */
+  int path;                   /* 1 = warp-resident DMMA (D <= 16), 2 = tiled DMMA GEMM (D > 16),
+                                 3 = pure-state vector sweep (D > 16, see QOC_FLAG_NO_PURE_STATE) */
   float main_kernel_ms_avg;   /* mean device time of the dominant kernel over the evaluations since the previous
                                  qoc_get_stats call (CUDA events on the launching stream, at most 64 samples) */
   int main_kernel_samples;

@@ -17,6 +17,7 @@ Base.@kwdef struct GPUGRAPE{OPTS}
     gradient::Symbol = :first_order        # :first_order (GRAPE) | :exact (ADGRAPE semantics)
     convention::Symbol = :inplace          # UnitaryGate sign: grad_func! (:inplace) | grad_func (:static)
     device::Int = 0
+    pure_state::Bool = true                # D > 16 pure-state transfers on sparse closed systems: vector sweep, same F and G
     optim_options::OPTS = Optim.Options()
 end
 
@@ -33,7 +34,7 @@ function _qoc_solve(members, wts, guess, alg::GPUGRAPE)
     p1 = members[1]
     D = size(p1.A, 1); K = p1.n_controls; N = alg.n_slices; M = length(members)
     desc = QocDesc(_code(p1.sys_type), D, K, N, M, 1, p1.T, alg.gradient == :exact ? 1 : 0,
-                   alg.convention == :static ? 1 : 0, alg.device, 0.0, 0)
+                   alg.convention == :static ? 1 : 0, alg.device, 0.0, alg.pure_state ? 0 : 1)   # flags: QOC_FLAG_NO_PURE_STATE = 1
     href = Ref{Ptr{Cvoid}}(C_NULL)
     _check(C_NULL, ccall((:qoc_create, libqoc), Cint, (Ref{Ptr{Cvoid}}, Ref{QocDesc}), href, desc))
     h = href[]

@@ -6,6 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QOCGRAPE_LIB") or os.path.join(HERE, "libqocgrape.so")   # env override: tuning builds
 
 QOC_OK, QOC_EINVAL, QOC_ECUDA, QOC_ENOMEM, QOC_EUNSUPPORTED = 0, 1, 2, 3, 4
+QOC_FLAG_NO_PURE_STATE = 1
 STATE_TRANSFER, UNITARY_GATE, COHERENCE_TRANSFER = 0, 1, 2
 GRAD_FIRST_ORDER, GRAD_EXACT = 0, 1
 REF_INPLACE, REF_STATIC = 0, 1

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include "../../include/qocgrape.h"
 #include "zgemm_dmma.cuh"
+#include "pure_state.cuh"
 
 namespace qoc {
 
@@ -178,6 +179,7 @@ struct BigState {
   std::vector<size_t> coo_member_off;
   long long ws = 0;
   bool attr_set = false;
+  PureState pure;                 // vector fast path for pure-state transfers on sparse closed systems (pure_state.cuh)
 };
 
 #define BIG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); \
@@ -189,7 +191,7 @@ template <class T> static int big_alloc(BigState* s, T** p, size_t n, std::strin
   s->ws += (long long)(n * sizeof(T));
   return QOC_OK;
 }
-static inline long long big_workspace(BigState* s) { return s ? s->ws : 0; }
+static inline long long big_workspace(BigState* s) { return s ? s->ws + s->pure.ws : 0; }
 
 static inline void big_destroy(BigState* s) {
   if (!s) return;
@@ -204,6 +206,7 @@ static inline void big_destroy(BigState* s) {
   if (s->evFork) cudaEventDestroy(s->evFork);
   if (s->evA) cudaEventDestroy(s->evA);
   if (s->evB) cudaEventDestroy(s->evB);
+  pure_free(s->pure);
   delete s;
 }
 
@@ -302,7 +305,7 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
   const int M = d.M, K = d.K, D = d.D;
   const size_t dd = (size_t)D * D;
   int rc;
-  s->batch_c0 = -1;
+  s->batch_c0 = -1; s->pure.batch_c0 = -1;
   auto rep = [&](double2* dst, const double* src, size_t per_member, bool sh) -> int {
     for (int k = 0; k < M; k++)
       if ((rc = big_upload_padded(s, dst + (size_t)k * per_member * s->DD, src + (sh ? 0 : (size_t)k * per_member * 2 * dd), per_member, err))) return rc;
@@ -352,7 +355,7 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
     BIG_CUDA(cudaMemcpy(s->coo_idx, idx.data(), idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
     BIG_CUDA(cudaMemcpy(s->coo_val, val.data(), val.size() * sizeof(double2), cudaMemcpyHostToDevice));
   }
-  return QOC_OK;
+  return pure_setup(s->pure, d, A, B, Xi, Xt, shared, s->herm != 0, err);
 }
 
 // ---------------------------------------------------------------------------------------------- launches
@@ -703,8 +706,44 @@ static int big_eval_member(BigState* s, int want_grad, cudaStream_t st, std::str
   return QOC_OK;
 }
 
+// Pure-state fast path: one sweep kernel (forward and backward CTAs of every chain), one gradient kernel, one fold.
+static int pure_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
+                     std::string& err, qoc_stats& stats) {
+  PureState& ps = s->pure;
+  const qoc_desc& d = s->d;
+  const int NK = d.N * d.K, total = d.M * d.R, M = d.M;
+  for (int c0 = 0; c0 < total; c0 += ps.cap) {
+    const int nb = std::min(ps.cap, total - c0);
+    if (c0 != ps.batch_c0 || nb != ps.batch_nb) {
+      std::vector<int> mem(nb), pul(nb), coo(nb);
+      for (int q = 0; q < nb; q++) { mem[q] = (c0 + q) % M; pul[q] = (c0 + q) / M; coo[q] = (int)s->coo_member_off[mem[q]]; }
+      BIG_CUDA(cudaMemcpyAsync(ps.member, mem.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+      BIG_CUDA(cudaMemcpyAsync(ps.pulse, pul.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+      BIG_CUDA(cudaMemcpyAsync(ps.coo_off, coo.data(), nb * sizeof(int), cudaMemcpyHostToDevice, st));
+      BIG_CUDA(cudaStreamSynchronize(st));
+      ps.batch_c0 = c0; ps.batch_nb = nb;
+    }
+    PureParams pp{};
+    pp.D = d.D; pp.K = d.K; pp.N = d.N; pp.tpr_log2 = ps.tpr_log2; pp.nthreads = ps.nthreads; pp.dt = d.T / d.N;
+    pp.ucol = ps.ucol; pp.cj = ps.cj; pp.cval = ps.cval; pp.mstruct = ps.mstruct; pp.psi0 = ps.psi0; pp.phi0 = ps.phi0;
+    pp.x = x_dev; pp.member = ps.member; pp.pulse = ps.pulse; pp.psi = ps.psi; pp.chi = ps.chi;
+    ps.kernel<<<dim3(2, nb), ps.nthreads, ps.smem, st>>>(pp);
+    BIG_COUNT();
+    PureGradParams gp{};
+    gp.D = d.D; gp.K = d.K; gp.N = d.N; gp.dt = d.T / d.N; gp.invD2 = 1.0 / ((double)d.D * d.D);
+    gp.psi = ps.psi; gp.chi = ps.chi; gp.coo_ptr_all = s->coo_ptr; gp.coo_off = ps.coo_off; gp.coo_idx = s->coo_idx; gp.coo_val = s->coo_val;
+    gp.g = ps.g; gp.tau_fom = ps.tau_fom; gp.want_grad = want_grad && d.K > 0; gp.t0 = gp.want_grad ? 0 : d.N - 1;
+    pure_grad_kernel<<<dim3(gp.want_grad ? d.N : 1, nb), 256, (size_t)2 * d.D * sizeof(double2), st>>>(gp);
+    BIG_COUNT();
+    big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev, ps.tau_fom, ps.g, wts_dev, ps.member, ps.pulse, nb, NK, want_grad);
+    BIG_COUNT();
+  }
+  return QOC_OK;
+}
+
 static inline int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
                            std::string& err, qoc_stats& stats) {
+  if (s->pure.active) return pure_eval(s, x_dev, FG_dev, want_grad, wts_dev, st, err, stats);
   const qoc_desc& d = s->d;
   const int NK = d.N * d.K, total = d.M * d.R;
   const bool batched = s->herm && !s->exact && want_grad;     // closed-system recursion: Bc chains per pass

@@ -216,7 +216,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     int rc = big_create(&h->big, d, h->err, h->ws_bytes);
     if (rc != QOC_OK) return fail(rc);
   }
-  h->red_chunk = 64;
+  h->red_chunk = std::max(4, (d.M + RED_MAX_CHUNKS - 1) / RED_MAX_CHUNKS);
   h->red_nchunks = (d.M + h->red_chunk - 1) / h->red_chunk;
   CR(dev_alloc(h, &h->wts, (size_t)d.M));
   CR(dev_alloc(h, &h->x, (size_t)d.R * h->NK));
@@ -280,7 +280,7 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->path == 2) {
     int rc = big_set_system(h->big, A, B, Xi, Xt, shared_flags, h->err);
-    if (rc == QOC_OK) h->system_set = true;
+    if (rc == QOC_OK) { h->system_set = true; h->st.path = h->big->pure.active ? 3 : 2; }
     return rc;
   }
   // small path: stage raw matrices on the device, then pack into the warp layout
@@ -509,10 +509,12 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   }
   if (!h->in_capture) { QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st)); h->kring_count++; }
   dim3 g1((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R), h->red_nchunks);
-  reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->part, d.M, h->NK, h->red_chunk, h->red_nchunks);
+  reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->red_nchunks == 1 ? fg_dev : h->part, d.M, h->NK,
+                                           h->red_chunk, h->red_nchunks);
   if ((rc = launch_check(h, "reduce_members_pass1")) != QOC_OK) return rc;
-  dim3 g2((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R));
-  reduce_members_pass2<<<g2, 256, 0, st>>>(h->part, fg_dev, h->NK, h->red_nchunks);
+  if (h->red_nchunks == 1) return QOC_OK;
+  dim3 g2((unsigned)(((h->NK + 1 + 31) / 32) * (long)d.R));
+  reduce_members_pass2<<<g2, 32 * RED_LANES, 0, st>>>(h->part, fg_dev, h->NK, h->red_nchunks);
   return launch_check(h, "reduce_members_pass2");
 }
 

@@ -564,7 +564,10 @@ __global__ void pack_kernel(const PackParams p) {
 }
 
 // Deterministic weighted ensemble reduction  F[r] = sum_k w_k fom[r,k],  G[r,:] = sum_k w_k grad[r,k,:]
-// (/root/reference/src/solve.jl:171-191), two fixed-order passes.
+// (/root/reference/src/solve.jl:171-191), two fixed-order passes: pass 1 folds `chunk` consecutive members (k ascending)
+// into one of at most RED_MAX_CHUNKS partial rows, pass 2 folds the partial rows (8 interleaved lanes per element, then a
+// fixed-order combine).  With a single chunk pass 1 writes the result itself (part == out, no pass 2).
+constexpr int RED_MAX_CHUNKS = 128, RED_LANES = 8;
 __global__ void reduce_members_pass1(const double* __restrict__ gradc, const double* __restrict__ fomc,
                                      const double* __restrict__ wts, double* __restrict__ part,
                                      int M, int NK, int chunk, int nchunks) {
@@ -577,17 +580,30 @@ __global__ void reduce_members_pass1(const double* __restrict__ gradc, const dou
   int k0 = ch * chunk, k1 = min(M, k0 + chunk);
   double s = 0.0;
   if (e == 0) { for (int k = k0; k < k1; k++) s += wts[k] * fomc[(size_t)r * M + k]; }
-  else if (gradc) { for (int k = k0; k < k1; k++) s += wts[k] * gradc[((size_t)r * M + k) * NK + (e - 1)]; }
+  else if (gradc) {
+    const double* g = gradc + (size_t)r * M * NK + (e - 1);
+#pragma unroll 4
+    for (int k = k0; k < k1; k++) s += wts[k] * __ldg(g + (size_t)k * NK);
+  }
   part[((size_t)r * nchunks + ch) * (NK + 1) + e] = s;
 }
-__global__ void reduce_members_pass2(const double* __restrict__ part, double* __restrict__ out, int NK, int nchunks) {
-  const int bpr = (NK + 1 + blockDim.x - 1) / blockDim.x;
-  int r = blockIdx.x / bpr;
-  int e = (blockIdx.x - r * bpr) * blockDim.x + threadIdx.x;
-  if (e > NK) return;
+__global__ void __launch_bounds__(32 * RED_LANES) reduce_members_pass2(const double* __restrict__ part, double* __restrict__ out, int NK, int nchunks) {
+  // block: 32 elements x RED_LANES partial-row lanes; grid: ceil((NK+1)/32) * R
+  __shared__ double sm[RED_LANES][33];
+  const int bpr = (NK + 1 + 31) / 32;
+  const int r = blockIdx.x / bpr;
+  const int e = (blockIdx.x - r * bpr) * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
   double s = 0.0;
-  for (int ch = 0; ch < nchunks; ch++) s += part[((size_t)r * nchunks + ch) * (NK + 1) + e];
-  out[(size_t)r * (NK + 1) + e] = s;
+  if (e <= NK)
+    for (int ch = lane; ch < nchunks; ch += RED_LANES) s += part[((size_t)r * nchunks + ch) * (NK + 1) + e];
+  sm[lane][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lane == 0 && e <= NK) {
+    double t = sm[0][threadIdx.x];
+#pragma unroll
+    for (int l = 1; l < RED_LANES; l++) t += sm[l][threadIdx.x];
+    out[(size_t)r * (NK + 1) + e] = t;
+  }
 }
 
 }  // namespace qoc

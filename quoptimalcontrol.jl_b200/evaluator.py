@@ -23,7 +23,7 @@ class GrapeEvaluator:
     x has shape (K, N) like the reference's control_array, or (R, K, N) for a multi-start batch."""
 
     def __init__(self, members, T, n_slices, sys_type, wts=None, gradient="first_order",
-                 convention="inplace", n_pulses=1, device=0, expm_theta=0.0):
+                 convention="inplace", n_pulses=1, device=0, expm_theta=0.0, pure_state=True):
         self._h = C.c_void_p()
         self._lib = _lib.load()
         M = len(members)
@@ -35,7 +35,8 @@ class GrapeEvaluator:
         desc = _lib.QocDesc(sys_type=code, D=D, K=K, N=self.N, M=M, R=self.R, T=float(T),
                             gradient={"first_order": _lib.GRAD_FIRST_ORDER, "exact": _lib.GRAD_EXACT}[gradient],
                             convention={"inplace": _lib.REF_INPLACE, "static": _lib.REF_STATIC}[convention],
-                            device=int(device), expm_theta=float(expm_theta), flags=0)
+                            device=int(device), expm_theta=float(expm_theta),
+                            flags=0 if pure_state else _lib.QOC_FLAG_NO_PURE_STATE)
         rc = self._lib.qoc_create(C.byref(self._h), C.byref(desc))
         if rc != _lib.QOC_OK:
             msg = self._lib.qoc_last_error(None).decode()

@@ -70,12 +70,14 @@ def test_large_norm_squarings():
     assert_parity(F, G, Fo, Go, ftol=1e-9, gtol=1e-7)
 
 
+@pytest.mark.parametrize("pure_state", [False, True])
 @pytest.mark.parametrize("n,N", [(6, 40), (8, 6)])
-def test_config5_reduced(n, N):
+def test_config5_reduced(n, N, pure_state):
     cfg = qoc.configs.config5(N=N, n=n)
     A, B, Xi, Xt = cfg["members"][0]
-    with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"]) as ev:
+    with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"], pure_state=pure_state) as ev:
         F, G = ev.eval(cfg["x"])
+        assert ev.stats()["path"] == (3 if pure_state else 2)
     Fo, Go = orc.fom_and_gradient_grape(A, B, cfg["x"], cfg["T"], Xi, Xt, cfg["sys_type"])
     assert_parity(F, G, Fo, Go)
 
@@ -127,3 +129,70 @@ def test_exact_too_many_squarings_is_loud():
         with pytest.raises(qoc.QocError) as e:
             ev.eval(np.ones((1, 2)))
     assert e.value.status == qoc._lib.QOC_EUNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pure-state vector path (path 3): StateTransfer between rank-1 states on a sparse closed system
+def _spin_chain(n, seed, complex_states=True):
+    """n-qubit Ising chain with local x/y controls and random (complex) product-free pure states."""
+    cfg = qoc.configs.config5(N=4, n=n)
+    A, B, _, _ = cfg["members"][0]
+    rng = np.random.default_rng(seed)
+    D = 2 ** n
+    psi = rng.normal(size=D) + (1j * rng.normal(size=D) if complex_states else 0)
+    phi = rng.normal(size=D) + (1j * rng.normal(size=D) if complex_states else 0)
+    psi /= np.linalg.norm(psi); phi /= np.linalg.norm(phi)
+    return A, B, np.outer(psi, psi.conj()), np.outer(phi, phi.conj())
+
+
+@pytest.mark.parametrize("n,N,T", [(5, 9, 1.0), (6, 17, 2.5), (7, 5, 0.7), (5, 6, 60.0)])
+def test_pure_state_path_matches_oracle(n, N, T):
+    """T = 60 with 6 slices drives ||dt H|| to ~40: exercises the Taylor sub-stepping."""
+    A, B, Xi, Xt = _spin_chain(n, seed=40 + n)
+    K = len(B)
+    x = np.random.default_rng(n + N).uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER) as ev:
+        F, G = ev.eval(x)
+        F0, _ = ev.eval(x, want_grad=False)
+        assert ev.stats()["path"] == 3
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert_parity(F, G, Fo, Go)
+    assert_parity(F0, None, Fo, None)
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER, pure_state=False) as ev:
+        Fd, Gd = ev.eval(x)
+        assert ev.stats()["path"] == 2
+    assert_parity(F, G, Fd, Gd)
+
+
+def test_pure_state_ensemble_and_pulses():
+    n, N, T, M, R = 5, 8, 1.3, 3, 2
+    A, B, Xi, Xt = _spin_chain(n, seed=77)
+    members = []
+    for k in range(M):     # members differ in drift, control scale and states
+        _, _, Xik, Xtk = _spin_chain(n, seed=78 + k)
+        members.append((A * (1 + 0.1 * k), [b * (1 - 0.05 * k) for b in B], Xik, Xtk))
+    wts = [0.2, 0.5, 0.3]
+    xs = np.random.default_rng(3).uniform(-1, 1, (R, len(B), N))
+    with qoc.GrapeEvaluator(members, T, N, orc.STATE_TRANSFER, wts=wts, n_pulses=R) as ev:
+        F, G = ev.eval(xs)
+        assert ev.stats()["path"] == 3
+    for r in range(R):
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, xs[r], T, orc.STATE_TRANSFER)
+        assert_parity(F[r], G[r], Fo, Go)
+
+
+def test_pure_state_path_not_taken_when_it_does_not_apply():
+    n, N, T = 5, 4, 1.0
+    A, B, Xi, Xt = _spin_chain(n, seed=5)
+    x = np.random.default_rng(0).uniform(-1, 1, (len(B), N))
+    mixed = 0.5 * Xi + 0.5 * Xt                                  # rank 2
+    for members, sys_type in [([(A, B, mixed, Xt)], orc.STATE_TRANSFER),                 # mixed initial state
+                              ([(A, B, Xi, Xt)], orc.COHERENCE_TRANSFER),                # other problem type
+                              ([random_system(32, 2, seed=1)], orc.STATE_TRANSFER)]:     # dense system
+        xk = np.random.default_rng(0).uniform(-1, 1, (len(members[0][1]), N))
+        with qoc.GrapeEvaluator(members, T, N, sys_type) as ev:
+            F, G = ev.eval(xk)
+            assert ev.stats()["path"] == 2
+        Am, Bm, Xim, Xtm = members[0]
+        Fo, Go = orc.fom_and_gradient_grape(Am, Bm, xk, T, Xim, Xtm, sys_type)
+        assert_parity(F, G, Fo, Go)
