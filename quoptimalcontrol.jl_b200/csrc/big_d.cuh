@@ -155,7 +155,8 @@ struct BigState {
   int Dp = 0, BT = 64, Cn = 1, Lmax = 1, unitary = 0;   // BT: CTA tile edge of the GEMM kernel (64, or 32 when that pads D tighter)
   // Chains (pulse r, member k) are evaluated Bc at a time: chain q of a batch owns slots [q*(N+1), (q+1)*(N+1)) of every
   // per-slice buffer and chunks [q*Cn, (q+1)*Cn), so all launches simply get a Bc times larger batch dimension.
-  int Bc = 1, tabw = 1;
+  int Bc = 1, tabw = 1, CnMax = 1;
+  long long ws_tables = 0;
   int batch_c0 = -1, batch_nb = 0;                      // batch currently described on the device (reset by set_system)
   int *chain_member = nullptr, *chain_pulse = nullptr, *chain_coo = nullptr;   // device [Bc]
   double2 *XiQ = nullptr, *XtQ = nullptr;                                     // per-chain copies of Xi, Xt for the batch
@@ -179,6 +180,8 @@ struct BigState {
   std::vector<size_t> coo_member_off;
   long long ws = 0;
   bool attr_set = false;
+  std::vector<int*> scan_tab;     // closed-system boundary scan: level l lists the chunk columns q*Cn + c with c >= 2^l
+  int *bndW0 = nullptr, *bndU = nullptr, *bndOut = nullptr;   // chunk-boundary conjugations: slot of W_0, column of U_c, slot of W[start_{c+1}]
   PureState pure;                 // vector fast path for pure-state transfers on sparse closed systems (pure_state.cuh)
 };
 
@@ -193,14 +196,16 @@ template <class T> static int big_alloc(BigState* s, T** p, size_t n, std::strin
 }
 static inline long long big_workspace(BigState* s) { return s ? s->ws + s->pure.ws : 0; }
 
+static inline void big_free_tables(BigState* s);
 static inline void big_destroy(BigState* s) {
   if (!s) return;
-  void* ptrs[] = {s->chain_member, s->chain_pulse, s->chain_coo, s->XiQ, s->XtQ, s->A, s->B, s->Xi, s->Xt, s->Q, s->T, s->tmpF, s->tmpB, s->tab2A, s->tab2T, s->tab0, s->tab4F, s->tab4B,
+  void* ptrs[] = {s->chain_member, s->chain_pulse, s->chain_coo, s->XiQ, s->XtQ, s->A, s->B, s->Xi, s->Xt, s->Q, s->T, s->tmpF, s->tmpB,
                   s->s_dev, s->norms, s->tau_fom, s->gk, s->coo_ptr, s->coo_idx, s->coo_val};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& b : s->buf) if (b) cudaFree(b);
   for (auto& b : s->xbuf) if (b) cudaFree(b);
   for (auto& b : s->pchain) if (b) cudaFree(b);
+  big_free_tables(s);
   if (s->sA) cudaStreamDestroy(s->sA);
   if (s->sB) cudaStreamDestroy(s->sB);
   if (s->evFork) cudaEventDestroy(s->evFork);
@@ -210,63 +215,43 @@ static inline void big_destroy(BigState* s) {
   delete s;
 }
 
-static inline int big_create(BigState** out, const qoc_desc& d, std::string& err, long long& ws_total) {
-  BigState* s = new BigState();
-  *out = s;
-  s->d = d;
-  s->exact = d.gradient == QOC_GRAD_EXACT;
-  { const int d32 = ((d.D + 31) / 32) * 32; if (d32 % 64 == 32) { s->BT = 32; s->Dp = d32; } else { s->BT = 64; s->Dp = ((d.D + 63) / 64) * 64; } }
-  s->DD = (size_t)s->Dp * s->Dp;
-  s->unitary = d.sys_type == QOC_UNITARY_GATE;
-  // chunking: (Dp/64)^2 tiles per GEMM; aim at one full wave of 2 CTAs/SM (296 CTAs) per lock-step launch
-  int tiles = (s->Dp / s->BT) * (s->Dp / s->BT);
-  int Cn = std::max(1, 296 / tiles);   // one full wave (2 CTAs/SM) per lock-step launch: measured best of {18, 37, 74} at D = 256
-  // small tiles counts: the 2*Cn sequential boundary launches would dominate; launches ~ 2 Cn + 3 N / Cn is minimal at sqrt(1.5 N)
-  Cn = std::min(Cn, std::max(1, (int)std::sqrt(1.5 * d.N)));
+// Chunk count.  General path: one full wave of 2 CTAs/SM per lock-step launch, capped where the 2 Cn sequential boundary
+// launches would dominate (launches ~ 2 Cn + 3 N / Cn is minimal at sqrt(1.5 N)).  Closed systems get their boundaries from a
+// parallel prefix (log2 Cn launches, Cn (log2 Cn + 2) extra products per chain): enough chunks to fill a wave together with
+// the Bc chains of a batch, otherwise enough to keep the lock-step loop at ~32 launches unless the prefix would cost more than
+// a tenth of the 7 N products.  Measured best for single chains (N = 2000): 296 / 74 / 37-74 chunks at D = 64 / 128 / 256.
+static inline int big_chunk_policy(const BigState* s, bool closed) {
+  const int tiles = (s->Dp / s->BT) * (s->Dp / s->BT), N = s->d.N;
+  int Cn = std::max(1, 296 / tiles);
+  if (closed) {
+    const int fill = (296 + tiles * s->Bc - 1) / (tiles * s->Bc);
+    int cap = 1;
+    while ((cap + 1) * (std::log2((double)(cap + 1)) + 2.0) <= 0.7 * N) cap++;
+    Cn = std::max(fill, std::min(N / 32, cap));
+  } else Cn = std::min(Cn, std::max(1, (int)std::sqrt(1.5 * N)));
   if (const char* e = getenv("QOC_BIG_CHUNKS")) Cn = std::max(1, atoi(e));   // tuning override
-  Cn = std::min(Cn, std::max(1, d.N / 2));
+  return std::max(1, std::min(Cn, std::max(1, N / 2)));
+}
+
+static inline void big_free_tables(BigState* s) {
+  for (int** t : {&s->tab2A, &s->tab2T, &s->tab0, &s->tab4F, &s->tab4B, &s->bndW0, &s->bndU, &s->bndOut}) { if (*t) cudaFree(*t); *t = nullptr; }
+  for (auto& b : s->scan_tab) if (b) cudaFree(b);
+  s->scan_tab.clear();
+  s->ws -= s->ws_tables; s->ws_tables = 0;
+}
+
+// chunk geometry and the lock-step / scan index tables for Cn chunks per chain (Cn <= CnMax)
+static int big_build_chunks(BigState* s, int Cn, std::string& err) {
+  const qoc_desc& d = s->d;
+  big_free_tables(s);
+  const long long ws0 = s->ws;
   s->Cn = Cn;
   s->start.resize(Cn); s->len.resize(Cn);
   for (int c = 0; c < Cn; c++) { int lo = (int)((long)c * d.N / Cn), hi = (int)((long)(c + 1) * d.N / Cn); s->start[c] = lo; s->len[c] = hi - lo; }
   s->Lmax = *std::max_element(s->len.begin(), s->len.end());
-  int rc;
-  BIG_CUDA(cudaStreamCreateWithFlags(&s->sA, cudaStreamNonBlocking));
-  BIG_CUDA(cudaStreamCreateWithFlags(&s->sB, cudaStreamNonBlocking));
-  BIG_CUDA(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
-  BIG_CUDA(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
-  BIG_CUDA(cudaEventCreateWithFlags(&s->evB, cudaEventDisableTiming));
-  const size_t DD = s->DD;
-  {  // batch size: as many chains as fit in half of the free device memory (exact mode keeps its many intermediates per chain)
-    size_t fre = 0, tot = 0;
-    BIG_CUDA(cudaMemGetInfo(&fre, &tot));
-    const double per_chain = 7.5 * (double)(d.N + 1) * DD * sizeof(double2);
-    long bc = (long)(0.5 * (double)fre / per_chain);
-    bc = std::max(1L, std::min(std::min(bc, 16384L), (long)d.M * d.R));
-    if (s->exact) bc = 1;
-    if (const char* e = getenv("QOC_BIG_BATCH")) bc = std::max(1L, std::min((long)atoi(e), (long)d.M * d.R));
-    s->Bc = (int)bc;
-  }
   const int Bc = s->Bc;
   s->tabw = Bc * Cn;
-  if ((rc = big_alloc(s, &s->A, (size_t)d.M * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->B, (size_t)d.M * std::max(d.K, 1) * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->Xi, (size_t)d.M * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->Xt, (size_t)d.M * DD, err))) return rc;
-  for (auto& b : s->buf) if ((rc = big_alloc(s, &b, (size_t)Bc * (d.N + 1) * DD, err))) return rc;
-  if (s->exact) for (auto& b : s->xbuf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->Q, (size_t)2 * Bc * Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->T, (size_t)Bc * Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->tmpF, (size_t)Bc * Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->tmpB, (size_t)Bc * Cn * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->XiQ, (size_t)Bc * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->XtQ, (size_t)Bc * DD, err))) return rc;
-  if ((rc = big_alloc(s, &s->chain_member, (size_t)Bc, err))) return rc;
-  if ((rc = big_alloc(s, &s->chain_pulse, (size_t)Bc, err))) return rc;
-  if ((rc = big_alloc(s, &s->chain_coo, (size_t)Bc, err))) return rc;
-  if ((rc = big_alloc(s, &s->s_dev, 1, err))) return rc;
-  if ((rc = big_alloc(s, &s->norms, (size_t)Bc * (d.N + 1), err))) return rc;
-  if ((rc = big_alloc(s, &s->tau_fom, (size_t)Bc * 4, err))) return rc;
-  if ((rc = big_alloc(s, &s->gk, (size_t)Bc * d.N * std::max(d.K, 1), err))) return rc;
+  int rc;
   // lock-step index tables over the virtual chain: row j, column q*Cn + c; entries are virtual slot indices q*(N+1) + t
   const int L = s->Lmax, W_ = s->tabw, N1 = d.N + 1;
   std::vector<int> t2A((size_t)L * W_, -1), t2T((size_t)L * W_, -1), t0(W_), t4F((size_t)L * W_, -1), t4B((size_t)L * W_, -1);
@@ -286,6 +271,71 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
     return QOC_OK;
   };
   if ((rc = up(&s->tab2A, t2A)) || (rc = up(&s->tab2T, t2T)) || (rc = up(&s->tab0, t0)) || (rc = up(&s->tab4F, t4F)) || (rc = up(&s->tab4B, t4B))) return rc;
+  // closed-system boundaries by a parallel prefix over the chunk totals (log2(Cn) batched launches instead of 3 Cn sequential ones)
+  for (int dd = 1; dd < Cn; dd <<= 1) {
+    std::vector<int> lv;
+    for (int q = 0; q < Bc; q++) for (int c = dd; c < Cn; c++) lv.push_back(q * Cn + c);
+    int* dev = nullptr;
+    if ((rc = up(&dev, lv))) return rc;
+    s->scan_tab.push_back(dev);
+  }
+  if (Cn > 1) {
+    std::vector<int> w0, uc, wo;
+    for (int q = 0; q < Bc; q++) for (int c = 0; c + 1 < Cn; c++) { w0.push_back(q * N1); uc.push_back(q * Cn + c); wo.push_back(q * N1 + s->start[c + 1]); }
+    if ((rc = up(&s->bndW0, w0)) || (rc = up(&s->bndU, uc)) || (rc = up(&s->bndOut, wo))) return rc;
+  }
+  s->ws_tables = s->ws - ws0;
+  return QOC_OK;
+}
+
+static inline int big_create(BigState** out, const qoc_desc& d, std::string& err, long long& ws_total) {
+  BigState* s = new BigState();
+  *out = s;
+  s->d = d;
+  s->exact = d.gradient == QOC_GRAD_EXACT;
+  { const int d32 = ((d.D + 31) / 32) * 32; if (d32 % 64 == 32) { s->BT = 32; s->Dp = d32; } else { s->BT = 64; s->Dp = ((d.D + 63) / 64) * 64; } }
+  s->DD = (size_t)s->Dp * s->Dp;
+  s->unitary = d.sys_type == QOC_UNITARY_GATE;
+  int rc;
+  BIG_CUDA(cudaStreamCreateWithFlags(&s->sA, cudaStreamNonBlocking));
+  BIG_CUDA(cudaStreamCreateWithFlags(&s->sB, cudaStreamNonBlocking));
+  BIG_CUDA(cudaEventCreateWithFlags(&s->evFork, cudaEventDisableTiming));
+  BIG_CUDA(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
+  BIG_CUDA(cudaEventCreateWithFlags(&s->evB, cudaEventDisableTiming));
+  const size_t DD = s->DD;
+  {  // batch size: as many chains as fit in half of the free device memory (exact mode keeps its many intermediates per chain)
+    size_t fre = 0, tot = 0;
+    BIG_CUDA(cudaMemGetInfo(&fre, &tot));
+    const double per_chain = (7.5 * (double)(d.N + 1) + 5.0 * std::min(296, std::max(1, d.N / 2))) * DD * sizeof(double2);
+    long bc = (long)(0.5 * (double)fre / per_chain);
+    bc = std::max(1L, std::min(std::min(bc, 16384L), (long)d.M * d.R));
+    if (s->exact) bc = 1;
+    if (const char* e = getenv("QOC_BIG_BATCH")) bc = std::max(1L, std::min((long)atoi(e), (long)d.M * d.R));
+    s->Bc = (int)bc;
+  }
+  const int Bc = s->Bc;
+  const int Cn = std::max(big_chunk_policy(s, false), big_chunk_policy(s, true));   // buffers are sized for the larger policy
+  s->CnMax = Cn;
+  if ((rc = big_alloc(s, &s->A, (size_t)d.M * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->B, (size_t)d.M * std::max(d.K, 1) * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Xi, (size_t)d.M * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Xt, (size_t)d.M * DD, err))) return rc;
+  for (auto& b : s->buf) if ((rc = big_alloc(s, &b, (size_t)Bc * (d.N + 1) * DD, err))) return rc;
+  if (s->exact) for (auto& b : s->xbuf) if ((rc = big_alloc(s, &b, (size_t)(d.N + 1) * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->Q, (size_t)2 * Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->T, (size_t)Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->tmpF, (size_t)Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->tmpB, (size_t)Bc * Cn * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->XiQ, (size_t)Bc * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->XtQ, (size_t)Bc * DD, err))) return rc;
+  if ((rc = big_alloc(s, &s->chain_member, (size_t)Bc, err))) return rc;
+  if ((rc = big_alloc(s, &s->chain_pulse, (size_t)Bc, err))) return rc;
+  if ((rc = big_alloc(s, &s->chain_coo, (size_t)Bc, err))) return rc;
+  if ((rc = big_alloc(s, &s->s_dev, 1, err))) return rc;
+  if ((rc = big_alloc(s, &s->norms, (size_t)Bc * (d.N + 1), err))) return rc;
+  if ((rc = big_alloc(s, &s->tau_fom, (size_t)Bc * 4, err))) return rc;
+  if ((rc = big_alloc(s, &s->gk, (size_t)Bc * d.N * std::max(d.K, 1), err))) return rc;
+  if ((rc = big_build_chunks(s, big_chunk_policy(s, false), err))) return rc;
   ws_total += s->ws;
   return QOC_OK;
 }
@@ -330,6 +380,8 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
     for (int k = 0; k < nB * K && h; k++) h = is_herm(B + 2 * (size_t)k * dd);
     s->herm = h ? 1 : 0;
     if (const char* e = getenv("QOC_BIG_HERM")) s->herm = s->herm && atoi(e) != 0;   // tuning / A-B testing override
+    const int want = std::min(big_chunk_policy(s, s->herm && !s->exact), s->CnMax);
+    if (want != s->Cn && (rc = big_build_chunks(s, want, err))) return rc;
   }
   // COO lists of the non-zeros of every control (indices in the padded matrix): tr(B W) = sum_nz B[a][b] W[b][a]
   std::vector<int> ptr; std::vector<int2> idx; std::vector<double2> val;
@@ -506,18 +558,24 @@ static int big_eval_batch_unitary(BigState* s, int nb, cudaStream_t st, std::str
   const int N = d.N, Cn = s->Cn, U = s->unitary;
   const long cs = (long)(N + 1) * (long)DD;          // chain stride in the per-slice buffers
   const long ts = (long)Cn * (long)DD;               // chain stride in the chunk-total buffer
-  const size_t half = (size_t)s->Bc * Cn * DD;
   int rc;
   double2 *P = s->Pfinal, *W = s->buf[3];
   GemmParams p{}; p.batch = nb; p.nout = 1;
-  // U_N = T_{Cn-1} ... T_0 per chain
-  const double2* Un = s->T; long us = ts;
-  for (int c = 1; c < Cn; c++) {
-    double2* dst = s->Q + (size_t)(c & 1) * half;
-    p.A = bmat(s->T + (size_t)c * DD, ts); p.B = bmat(Un, us); p.out[0] = eout(bmat(dst, sd));
-    if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-    Un = dst; us = sd;
+  // inclusive prefix products U_c = T_c ... T_0 of every chain (Kogge-Stone over the chunk columns, ping-pong T <-> Q)
+  double2* Us = s->T;
+  double2* Ud = s->Q;
+  {
+    int lvl = 0;
+    for (int dd = 1; dd < Cn; dd <<= 1, lvl++) {
+      GemmParams q{}; q.batch = nb * (Cn - dd); q.nout = 1;
+      q.A = bmat(Us, sd, s->scan_tab[lvl]); q.B = bmat(Us, sd, s->scan_tab[lvl], -dd); q.out[0] = eout(bmat(Ud, sd, s->scan_tab[lvl]));
+      if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+      BIG_CUDA(cudaMemcpy2DAsync(Ud, (size_t)ts * sizeof(double2), Us, (size_t)ts * sizeof(double2), (size_t)dd * DD * sizeof(double2), nb,
+                                 cudaMemcpyDeviceToDevice, st));           // columns c < dd are final already
+      std::swap(Us, Ud);
+    }
   }
+  const double2* Un = Us + (size_t)(Cn - 1) * DD; const long us = ts;      // U_N = U_{Cn-1}
   // C_0 = U_N' Xt (U_N)
   double2* C0 = s->tmpB;
   if (U) { p.A = bmat(Un, us); p.B = bmat(s->XtQ, sd); p.out[0] = eout(bmat(C0, sd)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc; }
@@ -536,12 +594,12 @@ static int big_eval_batch_unitary(BigState* s, int nb, cudaStream_t st, std::str
     p.A = bmat(C0, sd); p.B = bmat(s->XiQ, sd); p.out[0] = eout(bmat(W, cs), -1.0); eaux(p.out[0], bmat(W, cs), 1.0);
     if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
   }
-  // chunk-boundary operators W[start_{c+1}] = T_c W[start_c] T_c'
-  for (int c = 0; c + 1 < Cn; c++) {
-    GemmParams q{}; q.batch = nb; q.nout = 1;
-    q.A = bmat(W + (size_t)s->start[c] * DD, cs); q.B = bmat(s->T + (size_t)c * DD, ts); q.out[0] = eout(bmat(s->tmpF, sd));
+  // chunk-boundary operators W[start_{c+1}] = U_c W_0 U_c' for all chunks of all chains at once
+  if (Cn > 1) {
+    GemmParams q{}; q.batch = nb * (Cn - 1); q.nout = 1;
+    q.A = bmat(W, sd, s->bndW0); q.B = bmat(Us, sd, s->bndU); q.out[0] = eout(bmat(s->tmpF, sd));
     if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
-    q.A = bmat(s->T + (size_t)c * DD, ts); q.B = bmat(s->tmpF, sd); q.out[0] = eout(bmat(W + (size_t)(s->start[c] + s->len[c]) * DD, cs));
+    q.A = bmat(Us, sd, s->bndU); q.B = bmat(s->tmpF, sd); q.out[0] = eout(bmat(W, sd, s->bndOut));
     if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
   }
   // lock-step conjugation sweeps inside all chunks of all chains: W[t+1] = P_t W[t] P_t'

@@ -345,16 +345,23 @@ __global__ void __launch_bounds__(128) boundary_unitary_kernel(const PhasedParam
   double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
   const int Cn = p.Cn;
   const double2* T = p.totT + (size_t)w * Cn * E;
+  CM<NB> Tn = cm_load<NB>(L, T + (size_t)(Cn > 1 ? 1 : 0) * E);               // loads run one chunk ahead of the products
   CM<NB> Ut = transpose<NB>(L, cm_load<NB>(L, T), tb);                        // U^T after chunk 0
-  for (int c = 1; c < Cn; c++) Ut = mul_nt<NB>(Ut, cm_load<NB>(L, T + (size_t)c * E));   // U^T T_c^T
+  for (int c = 1; c < Cn; c++) {
+    const CM<NB> Tc = Tn;
+    if (c + 1 < Cn) Tn = cm_load<NB>(L, T + (size_t)(c + 1) * E);
+    Ut = mul_nt<NB>(Ut, Tc);                                                  // U^T T_c^T
+  }
   double fom;
   CM<NB> W = unitary_w0<NB, CPW, SYS>(L, Ut, cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E), cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E),
                                      p.sign_static, 1.0 / ((double)p.D * (double)p.D), tb, fom);
   if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
   double2* bW = p.bS + (size_t)w * (Cn + 1) * E;
   cm_store<NB>(L, bW, W);
+  Tn = cm_load<NB>(L, T);
   for (int c = 0; c + 1 < Cn; c++) {
-    const CM<NB> Tc = cm_load<NB>(L, T + (size_t)c * E);
+    const CM<NB> Tc = Tn;
+    if (c + 2 < Cn) Tn = cm_load<NB>(L, T + (size_t)(c + 1) * E);
     const CM<NB> X = mul_nt<NB, true, false>(Tc, W);
     W = mul_nt<NB>(Tc, X);
     cm_store<NB>(L, bW + (size_t)(c + 1) * E, W);
