@@ -182,6 +182,7 @@ struct BigState {
   bool attr_set = false;
   std::vector<int*> scan_tab;     // closed-system boundary scan: level l lists the chunk columns q*Cn + c with c >= 2^l
   int *bndW0 = nullptr, *bndU = nullptr, *bndOut = nullptr;   // chunk-boundary conjugations: slot of W_0, column of U_c, slot of W[start_{c+1}]
+  int *bndS0 = nullptr, *bndEnd = nullptr, *bndCN = nullptr;  // general path, per (chain, chunk): slot 0, slot end_c, slot N
   PureState pure;                 // vector fast path for pure-state transfers on sparse closed systems (pure_state.cuh)
 };
 
@@ -215,26 +216,23 @@ static inline void big_destroy(BigState* s) {
   delete s;
 }
 
-// Chunk count.  General path: one full wave of 2 CTAs/SM per lock-step launch, capped where the 2 Cn sequential boundary
-// launches would dominate (launches ~ 2 Cn + 3 N / Cn is minimal at sqrt(1.5 N)).  Closed systems get their boundaries from a
-// parallel prefix (log2 Cn launches, Cn (log2 Cn + 2) extra products per chain): enough chunks to fill a wave together with
-// the Bc chains of a batch, otherwise enough to keep the lock-step loop at ~32 launches unless the prefix would cost more than
-// a tenth of the 7 N products.  Measured best for single chains (N = 2000): 296 / 74 / 37-74 chunks at D = 64 / 128 / 256.
-static inline int big_chunk_policy(const BigState* s, bool closed) {
+// Chunk count.  Chunk-boundary operators come from parallel prefix / suffix products of the chunk totals (log2 Cn batched
+// launches, Cn (log2 Cn + 2) extra products per chain and direction): enough chunks to fill a wave of 2 CTAs/SM together
+// with the Bc chains of a batch, otherwise enough to keep the lock-step loops at ~32 launches unless the prefix would cost
+// more than a tenth of the per-slice products.  Measured best for single closed chains (N = 2000): 296 / 74 / 37-74 chunks
+// at D = 64 / 128 / 256.
+static inline int big_chunk_policy(const BigState* s) {
   const int tiles = (s->Dp / s->BT) * (s->Dp / s->BT), N = s->d.N;
-  int Cn = std::max(1, 296 / tiles);
-  if (closed) {
-    const int fill = (296 + tiles * s->Bc - 1) / (tiles * s->Bc);
-    int cap = 1;
-    while ((cap + 1) * (std::log2((double)(cap + 1)) + 2.0) <= 0.7 * N) cap++;
-    Cn = std::max(fill, std::min(N / 32, cap));
-  } else Cn = std::min(Cn, std::max(1, (int)std::sqrt(1.5 * N)));
+  const int fill = (296 + tiles * s->Bc - 1) / (tiles * s->Bc);
+  int cap = 1;
+  while ((cap + 1) * (std::log2((double)(cap + 1)) + 2.0) <= 0.7 * N) cap++;
+  int Cn = std::max(fill, std::min(N / 32, cap));
   if (const char* e = getenv("QOC_BIG_CHUNKS")) Cn = std::max(1, atoi(e));   // tuning override
   return std::max(1, std::min(Cn, std::max(1, N / 2)));
 }
 
 static inline void big_free_tables(BigState* s) {
-  for (int** t : {&s->tab2A, &s->tab2T, &s->tab0, &s->tab4F, &s->tab4B, &s->bndW0, &s->bndU, &s->bndOut}) { if (*t) cudaFree(*t); *t = nullptr; }
+  for (int** t : {&s->tab2A, &s->tab2T, &s->tab0, &s->tab4F, &s->tab4B, &s->bndW0, &s->bndU, &s->bndOut, &s->bndS0, &s->bndEnd, &s->bndCN}) { if (*t) cudaFree(*t); *t = nullptr; }
   for (auto& b : s->scan_tab) if (b) cudaFree(b);
   s->scan_tab.clear();
   s->ws -= s->ws_tables; s->ws_tables = 0;
@@ -284,6 +282,11 @@ static int big_build_chunks(BigState* s, int Cn, std::string& err) {
     for (int q = 0; q < Bc; q++) for (int c = 0; c + 1 < Cn; c++) { w0.push_back(q * N1); uc.push_back(q * Cn + c); wo.push_back(q * N1 + s->start[c + 1]); }
     if ((rc = up(&s->bndW0, w0)) || (rc = up(&s->bndU, uc)) || (rc = up(&s->bndOut, wo))) return rc;
   }
+  {
+    std::vector<int> s0, se, cn;
+    for (int q = 0; q < Bc; q++) for (int c = 0; c < Cn; c++) { s0.push_back(q * N1); se.push_back(q * N1 + s->start[c] + s->len[c]); cn.push_back(q * N1 + d.N); }
+    if ((rc = up(&s->bndS0, s0)) || (rc = up(&s->bndEnd, se)) || (rc = up(&s->bndCN, cn))) return rc;
+  }
   s->ws_tables = s->ws - ws0;
   return QOC_OK;
 }
@@ -314,7 +317,7 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
     s->Bc = (int)bc;
   }
   const int Bc = s->Bc;
-  const int Cn = std::max(big_chunk_policy(s, false), big_chunk_policy(s, true));   // buffers are sized for the larger policy
+  const int Cn = big_chunk_policy(s);
   s->CnMax = Cn;
   if ((rc = big_alloc(s, &s->A, (size_t)d.M * DD, err))) return rc;
   if ((rc = big_alloc(s, &s->B, (size_t)d.M * std::max(d.K, 1) * DD, err))) return rc;
@@ -335,7 +338,7 @@ static inline int big_create(BigState** out, const qoc_desc& d, std::string& err
   if ((rc = big_alloc(s, &s->norms, (size_t)Bc * (d.N + 1), err))) return rc;
   if ((rc = big_alloc(s, &s->tau_fom, (size_t)Bc * 4, err))) return rc;
   if ((rc = big_alloc(s, &s->gk, (size_t)Bc * d.N * std::max(d.K, 1), err))) return rc;
-  if ((rc = big_build_chunks(s, big_chunk_policy(s, false), err))) return rc;
+  if ((rc = big_build_chunks(s, Cn, err))) return rc;
   ws_total += s->ws;
   return QOC_OK;
 }
@@ -380,8 +383,6 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
     for (int k = 0; k < nB * K && h; k++) h = is_herm(B + 2 * (size_t)k * dd);
     s->herm = h ? 1 : 0;
     if (const char* e = getenv("QOC_BIG_HERM")) s->herm = s->herm && atoi(e) != 0;   // tuning / A-B testing override
-    const int want = std::min(big_chunk_policy(s, s->herm && !s->exact), s->CnMax);
-    if (want != s->Cn && (rc = big_build_chunks(s, want, err))) return rc;
   }
   // COO lists of the non-zeros of every control (indices in the padded matrix): tr(B W) = sum_nz B[a][b] W[b][a]
   std::vector<int> ptr; std::vector<int2> idx; std::vector<double2> val;
@@ -547,6 +548,33 @@ static int big_chunk_totals(BigState* s, int nb, cudaStream_t st, std::string& e
   return QOC_OK;
 }
 
+// Inclusive prefix (dir 0: U_c = T_c ... T_0) or suffix (dir 1: V_c = T_{Cn-1} ... T_c) products of the chunk totals of nb
+// chains, Kogge-Stone over the chunk columns: log2(Cn) batched launches.  `src` is only read; the levels ping-pong between
+// a and b.  *result holds the products, *spare is the other buffer (free for the caller).
+static int big_scan(BigState* s, int nb, int dir, const double2* src, double2* a, double2* b, const double2** result, double2** spare,
+                    cudaStream_t st, std::string& err, qoc_stats& stats) {
+  const size_t DD = s->DD; const long sd = (long)DD;
+  const int Cn = s->Cn;
+  const size_t pitch = (size_t)Cn * DD * sizeof(double2);
+  const double2* in = src;
+  double2* out = a;
+  int rc, lvl = 0;
+  for (int dd = 1; dd < Cn; dd <<= 1, lvl++) {
+    const int* tab = s->scan_tab[lvl];                      // columns q*Cn + c, c >= dd
+    GemmParams q{}; q.batch = nb * (Cn - dd); q.nout = 1;
+    if (dir == 0) { q.A = bmat(in, sd, tab); q.B = bmat(in, sd, tab, -dd); q.out[0] = eout(bmat(out, sd, tab)); }            // X_c X_{c-dd}
+    else          { q.A = bmat(in, sd, tab); q.B = bmat(in, sd, tab, -dd); q.out[0] = eout(bmat(out, sd, tab, -dd)); }       // X_{c+dd} X_c
+    if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
+    const size_t off = dir == 0 ? 0 : (size_t)(Cn - dd) * DD;                                                                // finished columns
+    BIG_CUDA(cudaMemcpy2DAsync(out + off, pitch, in + off, pitch, (size_t)dd * DD * sizeof(double2), nb, cudaMemcpyDeviceToDevice, st));
+    in = out;
+    out = out == a ? b : a;
+  }
+  *result = in;
+  *spare = out;
+  return QOC_OK;
+}
+
 // Closed systems (Hermitian drift and controls): every P_t is unitary, hence V_t = U_N U_t' and
 //   W_t = S_t C_t' (- C_t' S_t) = U_t W_0 U_t',   W_0 = Xi C_0' (- C_0' Xi),   C_0 = U_N' Xt (U_N).
 // One forward conjugation recursion W_{t+1} = P_t W_t P_t' replaces the separate state and costate sweeps and the
@@ -561,27 +589,16 @@ static int big_eval_batch_unitary(BigState* s, int nb, cudaStream_t st, std::str
   int rc;
   double2 *P = s->Pfinal, *W = s->buf[3];
   GemmParams p{}; p.batch = nb; p.nout = 1;
-  // inclusive prefix products U_c = T_c ... T_0 of every chain (Kogge-Stone over the chunk columns, ping-pong T <-> Q)
-  double2* Us = s->T;
-  double2* Ud = s->Q;
-  {
-    int lvl = 0;
-    for (int dd = 1; dd < Cn; dd <<= 1, lvl++) {
-      GemmParams q{}; q.batch = nb * (Cn - dd); q.nout = 1;
-      q.A = bmat(Us, sd, s->scan_tab[lvl]); q.B = bmat(Us, sd, s->scan_tab[lvl], -dd); q.out[0] = eout(bmat(Ud, sd, s->scan_tab[lvl]));
-      if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
-      BIG_CUDA(cudaMemcpy2DAsync(Ud, (size_t)ts * sizeof(double2), Us, (size_t)ts * sizeof(double2), (size_t)dd * DD * sizeof(double2), nb,
-                                 cudaMemcpyDeviceToDevice, st));           // columns c < dd are final already
-      std::swap(Us, Ud);
-    }
-  }
+  // inclusive prefix products U_c = T_c ... T_0 of every chain
+  const double2* Us; double2* tmp;
+  if ((rc = big_scan(s, nb, 0, s->T, s->Q, s->tmpF, &Us, &tmp, st, err, stats))) return rc;
   const double2* Un = Us + (size_t)(Cn - 1) * DD; const long us = ts;      // U_N = U_{Cn-1}
   // C_0 = U_N' Xt (U_N)
   double2* C0 = s->tmpB;
   if (U) { p.A = bmat(Un, us); p.B = bmat(s->XtQ, sd); p.out[0] = eout(bmat(C0, sd)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc; }
   else {
-    p.A = bmat(s->XtQ, sd); p.B = bmat(Un, us); p.out[0] = eout(bmat(s->tmpF, sd)); if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-    p.A = bmat(Un, us); p.B = bmat(s->tmpF, sd); p.out[0] = eout(bmat(C0, sd)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
+    p.A = bmat(s->XtQ, sd); p.B = bmat(Un, us); p.out[0] = eout(bmat(tmp, sd)); if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
+    p.A = bmat(Un, us); p.B = bmat(tmp, sd); p.out[0] = eout(bmat(C0, sd)); if ((rc = big_gemm(s, 1, 0, p, st, err, stats))) return rc;
   }
   // figure of merit: unitary tau = tr(S_N' Xt) = tr(Xi' C_0); density tau = tr(Xt' S_N) = tr(C_0' Xi)
   const double invD2 = 1.0 / ((double)d.D * d.D);
@@ -597,9 +614,9 @@ static int big_eval_batch_unitary(BigState* s, int nb, cudaStream_t st, std::str
   // chunk-boundary operators W[start_{c+1}] = U_c W_0 U_c' for all chunks of all chains at once
   if (Cn > 1) {
     GemmParams q{}; q.batch = nb * (Cn - 1); q.nout = 1;
-    q.A = bmat(W, sd, s->bndW0); q.B = bmat(Us, sd, s->bndU); q.out[0] = eout(bmat(s->tmpF, sd));
+    q.A = bmat(W, sd, s->bndW0); q.B = bmat(Us, sd, s->bndU); q.out[0] = eout(bmat(tmp, sd));
     if ((rc = big_gemm(s, 0, 1, q, st, err, stats))) return rc;
-    q.A = bmat(Us, sd, s->bndU); q.B = bmat(s->tmpF, sd); q.out[0] = eout(bmat(W, sd, s->bndOut));
+    q.A = bmat(Us, sd, s->bndU); q.B = bmat(tmp, sd); q.out[0] = eout(bmat(W, sd, s->bndOut));
     if ((rc = big_gemm(s, 0, 0, q, st, err, stats))) return rc;
   }
   // lock-step conjugation sweeps inside all chunks of all chains: W[t+1] = P_t W[t] P_t'
@@ -635,27 +652,25 @@ static int big_eval_member(BigState* s, int want_grad, cudaStream_t st, std::str
   BIG_CUDA(cudaEventRecord(s->evFork, st));
   BIG_CUDA(cudaStreamWaitEvent(s->sA, s->evFork, 0));
   BIG_CUDA(cudaStreamWaitEvent(s->sB, s->evFork, 0));
-  for (int c = 0; c < Cn; c++) {          // S[start_{c+1}] = T_c S[start_c] (T_c')
-    const double2* Tc = s->T + (size_t)c * DD;
-    double2* Sin = S + (size_t)s->start[c] * DD;
-    double2* Sout = S + (size_t)(s->start[c] + s->len[c]) * DD;
-    GemmParams p{}; p.batch = 1; p.nout = 1;
-    if (U) { p.A = bmat(Tc, 0); p.B = bmat(Sin, 0); p.out[0] = eout(bmat(Sout, 0)); if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc; }
+  {                                        // S[end_c] = U_c S_0 (U_c'),  U_c = T_c ... T_0, all chunks at once
+    const double2* Up; double2* tmp;
+    if ((rc = big_scan(s, 1, 0, s->T, s->Q, s->tmpF, &Up, &tmp, s->sA, err, stats))) return rc;
+    GemmParams p{}; p.batch = Cn; p.nout = 1;
+    if (U) { p.A = bmat(Up, sd); p.B = bmat(S, sd, s->bndS0); p.out[0] = eout(bmat(S, sd, s->bndEnd)); if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc; }
     else {
-      p.A = bmat(Sin, 0); p.B = bmat(Tc, 0); p.out[0] = eout(bmat(s->tmpF, 0)); if ((rc = big_gemm(s, 0, 1, p, s->sA, err, stats))) return rc;
-      p.A = bmat(Tc, 0); p.B = bmat(s->tmpF, 0); p.out[0] = eout(bmat(Sout, 0)); if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc;
+      p.A = bmat(S, sd, s->bndS0); p.B = bmat(Up, sd); p.out[0] = eout(bmat(tmp, sd)); if ((rc = big_gemm(s, 0, 1, p, s->sA, err, stats))) return rc;
+      p.A = bmat(Up, sd); p.B = bmat(tmp, sd); p.out[0] = eout(bmat(S, sd, s->bndEnd)); if ((rc = big_gemm(s, 0, 0, p, s->sA, err, stats))) return rc;
     }
   }
   if (want_grad) {
-    for (int c = Cn - 1; c >= 0; c--) {   // C[start_c] = T_c' C[end_c] (T_c)
-      const double2* Tc = s->T + (size_t)c * DD;
-      double2* Cin = C + (size_t)(s->start[c] + s->len[c]) * DD;
-      double2* Cout = C + (size_t)s->start[c] * DD;
-      GemmParams p{}; p.batch = 1; p.nout = 1;
-      if (U) { p.A = bmat(Tc, 0); p.B = bmat(Cin, 0); p.out[0] = eout(bmat(Cout, 0)); if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc; }
+    {                                      // C[start_c] = V_c' C_N (V_c),  V_c = T_{Cn-1} ... T_c
+      const double2* Vp; double2* tmp;
+      if ((rc = big_scan(s, 1, 1, s->T, s->Q + (size_t)s->Bc * Cn * DD, s->tmpB, &Vp, &tmp, s->sB, err, stats))) return rc;
+      GemmParams p{}; p.batch = Cn; p.nout = 1;
+      if (U) { p.A = bmat(Vp, sd); p.B = bmat(C, sd, s->bndCN); p.out[0] = eout(bmat(C, sd, s->tab0)); if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc; }
       else {
-        p.A = bmat(Cin, 0); p.B = bmat(Tc, 0); p.out[0] = eout(bmat(s->tmpB, 0)); if ((rc = big_gemm(s, 0, 0, p, s->sB, err, stats))) return rc;
-        p.A = bmat(Tc, 0); p.B = bmat(s->tmpB, 0); p.out[0] = eout(bmat(Cout, 0)); if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc;
+        p.A = bmat(C, sd, s->bndCN); p.B = bmat(Vp, sd); p.out[0] = eout(bmat(tmp, sd)); if ((rc = big_gemm(s, 0, 0, p, s->sB, err, stats))) return rc;
+        p.A = bmat(Vp, sd); p.B = bmat(tmp, sd); p.out[0] = eout(bmat(C, sd, s->tab0)); if ((rc = big_gemm(s, 1, 0, p, s->sB, err, stats))) return rc;
       }
     }
     // ---- phase 4: lock-step sweeps inside the chunks, forward on sA, backward on sB ----
@@ -851,20 +866,14 @@ static inline int big_propagators(BigState* s, const double* x_dev, double2* out
 static inline int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   const size_t DD = s->DD;
-  const size_t half = (size_t)s->Bc * s->Cn * DD;
   int rc;
   for (int c = 0; c < d.M * d.R; c++) {
     if ((rc = big_set_batch(s, c, 1, st, err))) return rc;
     if ((rc = big_propagators_phase(s, 1, x_dev, st, err, stats))) return rc;
     if ((rc = big_chunk_totals(s, 1, st, err, stats))) return rc;
-    const double2* cur = s->T;                       // U = T_{Cn-1} ... T_0
-    for (int j = 1; j < s->Cn; j++) {
-      double2* dst = s->Q + (size_t)(j & 1) * half;
-      GemmParams p{}; p.batch = 1; p.nout = 1;
-      p.A = bmat(s->T + (size_t)j * DD, 0); p.B = bmat(cur, 0); p.out[0] = eout(bmat(dst, 0));
-      if ((rc = big_gemm(s, 0, 0, p, st, err, stats))) return rc;
-      cur = dst;
-    }
+    const double2* Up; double2* spare;                // U = T_{Cn-1} ... T_0 = last inclusive prefix
+    if ((rc = big_scan(s, 1, 0, s->T, s->Q, s->tmpF, &Up, &spare, st, err, stats))) return rc;
+    const double2* cur = Up + (size_t)(s->Cn - 1) * DD;
     if ((rc = big_unpad(s, out + (size_t)c * d.D * d.D, cur, 1, st, err))) return rc;
   }
   return QOC_OK;
