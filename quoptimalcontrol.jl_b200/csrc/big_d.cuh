@@ -20,6 +20,7 @@
 #include "../../include/qocgrape.h"
 #include "zgemm_dmma.cuh"
 #include "pure_state.cuh"
+#include "small_d.cuh"      // reduce_members_pass1/2
 
 namespace qoc {
 
@@ -805,11 +806,22 @@ static int pure_eval(BigState* s, const double* x_dev, double* FG_dev, int want_
     PureGradParams gp{};
     gp.D = d.D; gp.K = d.K; gp.N = d.N; gp.dt = d.T / d.N; gp.invD2 = 1.0 / ((double)d.D * d.D);
     gp.psi = ps.psi; gp.chi = ps.chi; gp.coo_ptr_all = s->coo_ptr; gp.coo_off = ps.coo_off; gp.coo_idx = s->coo_idx; gp.coo_val = s->coo_val;
-    gp.g = ps.g; gp.tau_fom = ps.tau_fom; gp.want_grad = want_grad && d.K > 0; gp.t0 = gp.want_grad ? 0 : d.N - 1;
+    gp.g = ps.g; gp.tau_fom = ps.tau_fom; gp.fomc = ps.fomc; gp.want_grad = want_grad && d.K > 0; gp.t0 = gp.want_grad ? 0 : d.N - 1;
     pure_grad_kernel<<<dim3(gp.want_grad ? d.N : 1, nb), 256, (size_t)2 * d.D * sizeof(double2), st>>>(gp);
     BIG_COUNT();
-    big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev, ps.tau_fom, ps.g, wts_dev, ps.member, ps.pulse, nb, NK, want_grad);
-    BIG_COUNT();
+    if (nb == total) {       // every chain in one batch (chain = r * M + k): deterministic two-pass weighted member reduction
+      dim3 g1((unsigned)(((NK + 1 + 255) / 256) * (long)d.R), ps.red_nchunks);
+      reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? ps.g : nullptr, ps.fomc, wts_dev, ps.red_nchunks == 1 ? FG_dev : ps.part, M, NK,
+                                               ps.red_chunk, ps.red_nchunks);
+      BIG_COUNT();
+      if (ps.red_nchunks > 1) {
+        reduce_members_pass2<<<(unsigned)(((NK + 1 + 31) / 32) * (long)d.R), 32 * RED_LANES, 0, st>>>(ps.part, FG_dev, NK, ps.red_nchunks);
+        BIG_COUNT();
+      }
+    } else {
+      big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev, ps.tau_fom, ps.g, wts_dev, ps.member, ps.pulse, nb, NK, want_grad);
+      BIG_COUNT();
+    }
   }
   return QOC_OK;
 }

@@ -178,7 +178,7 @@ struct PureGradParams {
   int D, K, N; double dt, invD2;
   const double2 *psi, *chi;
   const int* coo_ptr_all; const int* coo_off; const int2* coo_idx; const double2* coo_val;
-  double* g; double* tau_fom; int want_grad; int t0;
+  double* g; double* tau_fom; double* fomc /* [chain], may be null */; int want_grad; int t0;
 };
 __global__ void __launch_bounds__(256) pure_grad_kernel(const PureGradParams p) {
   extern __shared__ double2 gsm2[];
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256) pure_grad_kernel(const PureGradParams p) 
     const double o2 = orr * orr + oi * oi;
     double* tf = p.tau_fom + (size_t)q * 4;
     tf[0] = o2; tf[1] = 0.0; tf[2] = 1.0 - o2 * o2 * p.invD2;
+    if (p.fomc) p.fomc[q] = tf[2];
   }
   if (!p.want_grad) return;
   const int* coo_ptr = p.coo_ptr_all + p.coo_off[q];
@@ -228,13 +229,14 @@ struct PureState {
   pure_kfn kernel = nullptr;
   int *ucol = nullptr, *cj = nullptr, *mstruct = nullptr, *member = nullptr, *pulse = nullptr, *coo_off = nullptr;
   double2 *cval = nullptr, *psi0 = nullptr, *phi0 = nullptr, *psi = nullptr, *chi = nullptr;
-  double *g = nullptr, *tau_fom = nullptr;
+  double *g = nullptr, *tau_fom = nullptr, *fomc = nullptr, *part = nullptr;   // part: partial rows of the member reduction
+  int red_chunk = 1, red_nchunks = 1;
   long long ws = 0;
   int batch_c0 = -1, batch_nb = 0;
 };
 
 static inline void pure_free(PureState& ps) {
-  void* ptrs[] = {ps.ucol, ps.cj, ps.mstruct, ps.member, ps.pulse, ps.coo_off, ps.cval, ps.psi0, ps.phi0, ps.psi, ps.chi, ps.g, ps.tau_fom};
+  void* ptrs[] = {ps.ucol, ps.cj, ps.mstruct, ps.member, ps.pulse, ps.coo_off, ps.cval, ps.psi0, ps.phi0, ps.psi, ps.chi, ps.g, ps.tau_fom, ps.fomc, ps.part};
   for (void* p : ptrs) if (p) cudaFree(p);
   ps = PureState();
 }
@@ -366,7 +368,11 @@ static inline int pure_setup(PureState& ps, const qoc_desc& d, const double* A, 
       (rc = pure_alloc(ps, &ps.mstruct, (size_t)M, err)) || (rc = pure_alloc(ps, &ps.member, (size_t)cap, err)) || (rc = pure_alloc(ps, &ps.pulse, (size_t)cap, err)) ||
       (rc = pure_alloc(ps, &ps.coo_off, (size_t)cap, err)) || (rc = pure_alloc(ps, &ps.psi0, (size_t)M * D, err)) || (rc = pure_alloc(ps, &ps.phi0, (size_t)M * D, err)) ||
       (rc = pure_alloc(ps, &ps.psi, (size_t)cap * (N + 1) * D, err)) || (rc = pure_alloc(ps, &ps.chi, (size_t)cap * (N + 1) * D, err)) ||
-      (rc = pure_alloc(ps, &ps.g, (size_t)cap * N * std::max(K, 1), err)) || (rc = pure_alloc(ps, &ps.tau_fom, (size_t)cap * 4, err))) return rc;
+      (rc = pure_alloc(ps, &ps.g, (size_t)cap * N * std::max(K, 1), err)) || (rc = pure_alloc(ps, &ps.tau_fom, (size_t)cap * 4, err)) ||
+      (rc = pure_alloc(ps, &ps.fomc, (size_t)cap, err))) return rc;
+  ps.red_chunk = std::max(4, (M + 127) / 128);            // same two-pass member reduction as the small-D path (<= 128 partial rows)
+  ps.red_nchunks = (M + ps.red_chunk - 1) / ps.red_chunk;
+  if ((rc = pure_alloc(ps, &ps.part, (size_t)d.R * ps.red_nchunks * ((size_t)N * K + 1), err))) return rc;
   PURE_CUDA(cudaMemcpy(ps.ucol, ucol.data(), ucol.size() * sizeof(int), cudaMemcpyHostToDevice));
   PURE_CUDA(cudaMemcpy(ps.cj, cj.data(), cj.size() * sizeof(int), cudaMemcpyHostToDevice));
   PURE_CUDA(cudaMemcpy(ps.cval, cval.data(), cval.size() * sizeof(double2), cudaMemcpyHostToDevice));
