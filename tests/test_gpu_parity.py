@@ -253,7 +253,7 @@ def test_c_abi_error_paths_and_stats():
     assert lib.qoc_eval(h, x.ctypes.data, F.ctypes.data, G.ctypes.data) == 0
     st = qoc._lib.QocStats()
     assert lib.qoc_get_stats(h, C.byref(st)) == 0
-    assert st.n_evals == 2 and st.launches_last_eval >= 3 and st.path == 1 and st.workspace_bytes > 0
+    assert st.n_evals == 2 and st.launches_last_eval >= 2 and st.path == 1 and st.workspace_bytes > 0   # chain kernel + reduction
     bad = qoc._lib.QocDesc(sys_type=0, D=4, K=2, N=6, M=1, R=1, T=1.0, device=99)
     h2 = C.c_void_p()
     assert lib.qoc_create(C.byref(h2), C.byref(bad)) == qoc._lib.QOC_EINVAL and not h2.value
