@@ -28,6 +28,9 @@ FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak.json")
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
 
 
+_OUT = sys.stdout
+
+
 def build_config(name):
     import quoptimalcontrol_jl_b200 as qoc
     c = qoc.configs
@@ -140,7 +143,7 @@ def run_reference(args, cfg, rank):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind_fn == "c" and M > 1 else (threads if kind_fn == "numpy" else 1),
                              "kind": "port", "sample": sample + ("; C restatement + OpenMP over members" if kind_fn == "c" else "; numpy/OpenBLAS restatement")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def main():
@@ -156,6 +159,12 @@ def main():
                     help="N > 1: fused one-shot all-reduce over NVLink peer memory (default) or torch.distributed NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly one JSON line: keep a private handle to it and point fd 1 at stderr, so that anything a
+    # library prints to stdout (e.g. the NCCL version banner) cannot end up in front of the result
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,7 +182,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     members, wts = cfg["members"], cfg["wts"]
@@ -432,7 +440,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
     if pure is not None:
         line["pure_state_path"] = pure
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
