@@ -53,3 +53,20 @@ def test_shard_bounds_cover_everything():
             assert parts[0][0] == 0 and parts[-1][1] == M
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             assert max(h - l for l, h in parts) - min(h - l for l, h in parts) <= 1
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU restatement, tier contract (4)): exactly one JSON line on stdout with the keys the
+    driver reads; nothing else may reach stdout."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "cfg1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "evals/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["workload"].startswith("cfg1")
