@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libqocgrape.so")
 SOURCES = ["qocgrape.cu"]
-HEADERS = ["warp_mat.cuh", "small_d.cuh", "small_phased.cuh", "big_d.cuh", "zgemm_dmma.cuh", os.path.join("..", "..", "include", "qocgrape.h")]
+HEADERS = ["warp_mat.cuh", "small_d.cuh", "small_phased.cuh", "big_d.cuh", "zgemm_dmma.cuh", "pure_state.cuh", os.path.join("..", "..", "include", "qocgrape.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]
 

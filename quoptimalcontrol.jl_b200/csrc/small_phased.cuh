@@ -11,6 +11,15 @@
 #pragma once
 #include "small_d.cuh"
 
+// resident CTAs (4 warps each) per SM requested for the D = 8 chunk kernels: 5 -> 96 registers per thread, 6 -> 80.
+// Measured on cfg4 (expm, sweep): (5,5) 2.437 ms, (5,6) 2.408, (6,5) 2.489, (6,6) 2.459, (7,7) 2.515 -- the exponential spills at 80.
+#ifndef QOC_EXPM_MINB
+#define QOC_EXPM_MINB 5
+#endif
+#ifndef QOC_SWEEP_MINB
+#define QOC_SWEEP_MINB 6
+#endif
+
 namespace qoc {
 
 struct PhasedParams {
@@ -278,7 +287,7 @@ __device__ __forceinline__ void chunk_expm_body(const PhasedParams& p, double2* 
   cm_store<NB>(L, p.totT + ((size_t)w * p.Cn + c) * E, transpose<NB>(L, Tt, tb));
 }
 template <int NB, int CPW>
-__global__ void __launch_bounds__(128, NB == 1 ? 5 : 1) chunk_expm_kernel(const PhasedParams p) {
+__global__ void __launch_bounds__(128, NB == 1 ? QOC_EXPM_MINB : 1) chunk_expm_kernel(const PhasedParams p) {
   extern __shared__ double2 smem[];
   if (p.sys_in_smem) chunk_expm_body<NB, CPW, true>(p, smem); else chunk_expm_body<NB, CPW, false>(p, smem);
 }
@@ -398,7 +407,7 @@ __device__ __forceinline__ void sweep_unitary_body(const PhasedParams& p, double
   }
 }
 template <int NB, int CPW>
-__global__ void __launch_bounds__(128, NB == 1 ? 5 : 1) sweep_unitary_kernel(const PhasedParams p) {
+__global__ void __launch_bounds__(128, NB == 1 ? QOC_SWEEP_MINB : 1) sweep_unitary_kernel(const PhasedParams p) {
   extern __shared__ double2 smem[];
   if (p.sys_in_smem) sweep_unitary_body<NB, CPW, true>(p, smem); else sweep_unitary_body<NB, CPW, false>(p, smem);
 }

@@ -69,7 +69,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 }
 
 template <int OPA, int OPB, int MI>
-__global__ void __launch_bounds__(GB_THREADS, 2) zgemm_dmma_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(GB_THREADS, MI == 2 ? 4 : 2) zgemm_dmma_kernel(const GemmParams p) {   // 32x32 tiles: 4 CTAs (49 KB each) per SM
   extern __shared__ double2 gsm[];
   constexpr int NJ = MI / 2;
   constexpr int GB_M = GemmGeom<MI>::BT, GB_N = GemmGeom<MI>::BT, GB_LD_KM = GemmGeom<MI>::LD_KM;
