@@ -196,3 +196,36 @@ def test_pure_state_path_not_taken_when_it_does_not_apply():
         Am, Bm, Xim, Xtm = members[0]
         Fo, Go = orc.fom_and_gradient_grape(Am, Bm, xk, T, Xim, Xtm, sys_type)
         assert_parity(F, G, Fo, Go)
+
+
+@pytest.mark.parametrize("D,K", [(24, 2), (40, 3), (17, 1)])
+def test_pure_state_path_general_sparse_system(D, K):
+    """Not a qubit register: banded complex Hermitian drift and controls (a few diagonals), D not a multiple of 32."""
+    rng = np.random.default_rng(D)
+    def banded(offsets):
+        Hm = np.zeros((D, D), dtype=complex)
+        for o in offsets:
+            v = rng.normal(size=D - o) + (1j * rng.normal(size=D - o) if o else 0)
+            Hm += np.diag(v, o) + (np.diag(v.conj(), -o) if o else 0)
+        return Hm
+    A = banded([0, 1])
+    B = [banded([1, 3]) if j % 2 == 0 else banded([2]) for j in range(K)]
+    psi = rng.normal(size=D) + 1j * rng.normal(size=D); psi /= np.linalg.norm(psi)
+    phi = rng.normal(size=D) + 1j * rng.normal(size=D); phi /= np.linalg.norm(phi)
+    Xi, Xt = np.outer(psi, psi.conj()), np.outer(phi, phi.conj())
+    N, T = 11, 0.9
+    x = rng.uniform(-1, 1, (K, N))
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER) as ev:
+        F, G = ev.eval(x)
+        assert ev.stats()["path"] == 3
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert_parity(F, G, Fo, Go)
+
+
+def test_pure_state_path_without_controls():
+    A, B, Xi, Xt = _spin_chain(5, seed=3)
+    with qoc.GrapeEvaluator([(A, [], Xi, Xt)], 1.0, 5, orc.STATE_TRANSFER) as ev:
+        F, G = ev.eval(np.zeros((0, 5)))
+        path = ev.stats()["path"]
+    Fo, _ = orc.fom_and_gradient_grape(A, [], np.zeros((0, 5)), 1.0, Xi, Xt, orc.STATE_TRANSFER)
+    assert path in (2, 3) and abs(F - Fo) <= 1e-10 * max(1.0, abs(Fo))
