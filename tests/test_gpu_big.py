@@ -198,9 +198,10 @@ def test_pure_state_path_not_taken_when_it_does_not_apply():
         assert_parity(F, G, Fo, Go)
 
 
-@pytest.mark.parametrize("D,K", [(24, 2), (40, 3), (17, 1)])
-def test_pure_state_path_general_sparse_system(D, K):
-    """Not a qubit register: banded complex Hermitian drift and controls (a few diagonals), D not a multiple of 32."""
+@pytest.mark.parametrize("D,K,path", [(24, 1, 3), (40, 3, 3), (36, 2, 3), (17, 1, 2), (24, 2, 2)])
+def test_pure_state_path_general_sparse_system(D, K, path):
+    """Not a qubit register: banded complex Hermitian drift and controls (a few diagonals), D not a multiple of 32.
+    The union pattern has 5 (K = 1) or 7 entries per row; with more than D/4 the dense path is kept (path 2)."""
     rng = np.random.default_rng(D)
     def banded(offsets):
         Hm = np.zeros((D, D), dtype=complex)
@@ -217,7 +218,7 @@ def test_pure_state_path_general_sparse_system(D, K):
     x = rng.uniform(-1, 1, (K, N))
     with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER) as ev:
         F, G = ev.eval(x)
-        assert ev.stats()["path"] == 3
+        assert ev.stats()["path"] == path
     Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
     assert_parity(F, G, Fo, Go)
 
