@@ -278,8 +278,14 @@ static inline int pure_setup(PureState& ps, const qoc_desc& d, const double* A, 
                              int shared, bool herm, std::string& err) {
   pure_free(ps);
   if (!herm || d.sys_type != QOC_STATE_TRANSFER || d.gradient != QOC_GRAD_FIRST_ORDER || (d.flags & QOC_FLAG_NO_PURE_STATE)) return QOC_OK;
-  if (const char* e = getenv("QOC_PURE_STATE")) if (atoi(e) == 0) return QOC_OK;
+  bool forced = false;
+  if (const char* e = getenv("QOC_PURE_STATE")) { if (atoi(e) == 0) return QOC_OK; forced = true; }
   const int D = d.D, K = d.K, M = d.M, N = d.N;
+  // The sweep is latency-bound (~12 dependent Taylor terms per slice, ~1.9 us per slice whatever D is) while chains are
+  // independent CTAs; the dense path needs 0.33 / 1.0 / 5 / 32 us per slice at D = 32 / 64 / 128 / 256 for one chain and
+  // grows with the number of chains.  Measured crossovers: always at D >= 128, from 3 chains at D = 64, from 16 below.
+  const long chains = (long)M * d.R;
+  if (!forced && !(D >= 128 || (D >= 64 && chains >= 3) || chains >= 16)) return QOC_OK;
   const size_t dd = (size_t)D * D;
   // pure states?
   const int nXi = (shared & QOC_SHARED_XI) ? 1 : M, nXt = (shared & QOC_SHARED_XT) ? 1 : M;

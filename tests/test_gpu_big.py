@@ -72,7 +72,8 @@ def test_large_norm_squarings():
 
 @pytest.mark.parametrize("pure_state", [False, True])
 @pytest.mark.parametrize("n,N", [(6, 40), (8, 6)])
-def test_config5_reduced(n, N, pure_state):
+def test_config5_reduced(monkeypatch, n, N, pure_state):
+    monkeypatch.setenv("QOC_PURE_STATE", "1" if pure_state else "0")      # "1": also below the size where the library picks it
     cfg = qoc.configs.config5(N=N, n=n)
     A, B, Xi, Xt = cfg["members"][0]
     with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"], pure_state=pure_state) as ev:
@@ -146,8 +147,9 @@ def _spin_chain(n, seed, complex_states=True):
 
 
 @pytest.mark.parametrize("n,N,T", [(5, 9, 1.0), (6, 17, 2.5), (7, 5, 0.7), (5, 6, 60.0)])
-def test_pure_state_path_matches_oracle(n, N, T):
+def test_pure_state_path_matches_oracle(monkeypatch, n, N, T):
     """T = 60 with 6 slices drives ||dt H|| to ~40: exercises the Taylor sub-stepping."""
+    monkeypatch.setenv("QOC_PURE_STATE", "1")
     A, B, Xi, Xt = _spin_chain(n, seed=40 + n)
     K = len(B)
     x = np.random.default_rng(n + N).uniform(-1, 1, (K, N))
@@ -158,13 +160,14 @@ def test_pure_state_path_matches_oracle(n, N, T):
     Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
     assert_parity(F, G, Fo, Go)
     assert_parity(F0, None, Fo, None)
-    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER, pure_state=False) as ev:
+    with qoc.GrapeEvaluator([(A, B, Xi, Xt)], T, N, orc.STATE_TRANSFER, pure_state=False) as ev:     # the flag wins over the env
         Fd, Gd = ev.eval(x)
         assert ev.stats()["path"] == 2
     assert_parity(F, G, Fd, Gd)
 
 
-def test_pure_state_ensemble_and_pulses():
+def test_pure_state_ensemble_and_pulses(monkeypatch):
+    monkeypatch.setenv("QOC_PURE_STATE", "1")
     n, N, T, M, R = 5, 8, 1.3, 3, 2
     A, B, Xi, Xt = _spin_chain(n, seed=77)
     members = []
@@ -181,7 +184,8 @@ def test_pure_state_ensemble_and_pulses():
         assert_parity(F[r], G[r], Fo, Go)
 
 
-def test_pure_state_path_not_taken_when_it_does_not_apply():
+def test_pure_state_path_not_taken_when_it_does_not_apply(monkeypatch):
+    monkeypatch.setenv("QOC_PURE_STATE", "1")
     n, N, T = 5, 4, 1.0
     A, B, Xi, Xt = _spin_chain(n, seed=5)
     x = np.random.default_rng(0).uniform(-1, 1, (len(B), N))
@@ -199,9 +203,10 @@ def test_pure_state_path_not_taken_when_it_does_not_apply():
 
 
 @pytest.mark.parametrize("D,K,path", [(24, 1, 3), (40, 3, 3), (36, 2, 3), (17, 1, 2), (24, 2, 2)])
-def test_pure_state_path_general_sparse_system(D, K, path):
+def test_pure_state_path_general_sparse_system(monkeypatch, D, K, path):
     """Not a qubit register: banded complex Hermitian drift and controls (a few diagonals), D not a multiple of 32.
     The union pattern has 5 (K = 1) or 7 entries per row; with more than D/4 the dense path is kept (path 2)."""
+    monkeypatch.setenv("QOC_PURE_STATE", "1")
     rng = np.random.default_rng(D)
     def banded(offsets):
         Hm = np.zeros((D, D), dtype=complex)
@@ -223,7 +228,22 @@ def test_pure_state_path_general_sparse_system(D, K, path):
     assert_parity(F, G, Fo, Go)
 
 
-def test_pure_state_path_without_controls():
+def test_pure_state_path_selection_by_size():
+    """Without the override the library keeps single small chains on the dense path and takes the vector path from D = 128,
+    from 3 chains at D = 64 and from 16 chains below."""
+    for n, M, want in [(5, 1, 2), (5, 16, 3), (6, 2, 2), (6, 3, 3), (7, 1, 3)]:
+        A, B, Xi, Xt = _spin_chain(n, seed=n)
+        members = [(A * (1 + 0.01 * k), B, Xi, Xt) for k in range(M)]
+        x = np.random.default_rng(n).uniform(-1, 1, (len(B), 3))
+        with qoc.GrapeEvaluator(members, 0.5, 3, orc.STATE_TRANSFER) as ev:
+            F, G = ev.eval(x)
+            assert ev.stats()["path"] == want, (n, M)
+        Fo, Go = orc.ensemble_fom_and_gradient(members, np.ones(M), x, 0.5, orc.STATE_TRANSFER)
+        assert_parity(F, G, Fo, Go)
+
+
+def test_pure_state_path_without_controls(monkeypatch):
+    monkeypatch.setenv("QOC_PURE_STATE", "1")
     A, B, Xi, Xt = _spin_chain(5, seed=3)
     with qoc.GrapeEvaluator([(A, [], Xi, Xt)], 1.0, 5, orc.STATE_TRANSFER) as ev:
         F, G = ev.eval(np.zeros((0, 5)))
