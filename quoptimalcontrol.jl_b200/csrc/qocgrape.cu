@@ -174,7 +174,8 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     // with the closed-system recursion (6 products per slice in either mode) 4 chunks per chain still win at full batch:
     // cfg4 4096 chains 2.44 ms vs 2.52 ms fused, 2048 chains 1.26 vs 1.50 ms
     if (!h->phased && !h->chunked && h->n_groups >= 1500 && d.N >= 64 && d.gradient == QOC_GRAD_FIRST_ORDER && !getenv("QOC_CHUNKED")) {
-      h->chunked_closed = 1; h->Cn = 4;
+      h->chunked_closed = 1; h->Cn = std::min(8, std::max(2, d.N / 16));   // measured 2 / 3 / 4 / 6 / 8 chunks at 4096 chains: 2.452 / 2.421 / 2.408 / 2.400 / 2.398 ms
+      if (const char* e = getenv("QOC_CHUNKS")) h->Cn = std::max(2, std::min(atoi(e), d.N / 2));   // tuning override
     }
     if (h->phased) {
       h->have_P = 1;
