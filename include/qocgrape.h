@@ -120,6 +120,16 @@ int qoc_total_propagator(qoc_handle* h, const double* x, double* U);
  * pw_gen_save! (:80-92) for mode 2:  out [R][M][N][D*D]. */
 int qoc_propagators(qoc_handle* h, const double* x, double* out, int mode);
 
+/* ---- slice-parallel evaluation of ONE large instance over several GPUs (SURVEY.md 8e "config 5", 8f rank 4) -------
+ * Each rank owns a contiguous range of slices and a handle created with that range's N and T (D > 16, M = R = 1,
+ * QOC_FLAG_NO_PURE_STATE).  Per evaluation: (1) qoc_total_propagator gives the range's propagator product U_r;
+ * (2) the ranks exchange the U_r (D x D each: the path's only exchange) and form their boundary operators, the state
+ * before and the costate after their range (pw_evolve semantics, src/GRAPE.jl:216-251 applied to whole ranges);
+ * (3) qoc_set_states installs them as Xi / Xt; (4) qoc_eval_continue finishes the evaluation from the propagators that
+ * step (1) left on the device: F is the full figure of merit, G [N_r][K] the gradient entries of the rank's slices. */
+int qoc_set_states(qoc_handle* h, const double* Xi, const double* Xt, int shared_flags);
+int qoc_eval_continue(qoc_handle* h, double* F, double* G);
+
 /* ---- multi-GPU, one process per GPU: fused one-shot all-reduce of [F|G] over NVLink peer memory -------------------
  * Replaces the cross-shard part of the ensemble reduction `sum(gradient .* wts, dims = 1)` (src/solve.jl:171-191) when
  * the members are sharded over GPUs.  Each rank publishes its weighted partial in a CUDA-IPC shared exchange buffer,

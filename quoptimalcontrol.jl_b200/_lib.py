@@ -15,7 +15,8 @@ IPC_HANDLE_BYTES = 64
 
 EXPORTS = ["qoc_version", "qoc_create", "qoc_destroy", "qoc_set_system", "qoc_eval", "qoc_eval_device",
            "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error",
-           "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device", "qoc_minimize_lbfgs"]
+           "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device", "qoc_minimize_lbfgs",
+           "qoc_set_states", "qoc_eval_continue"]
 
 
 class QocDesc(C.Structure):
@@ -74,6 +75,8 @@ def load():
     lib.qoc_comm_export.argtypes = [vp, vp]
     lib.qoc_comm_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.qoc_eval_allreduce_device.argtypes = [vp, vp, vp, C.c_int, vp]
+    lib.qoc_set_states.argtypes = [vp, vp, vp, C.c_int]
+    lib.qoc_eval_continue.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         if name not in ("qoc_version", "qoc_last_error"):
             getattr(lib, name).restype = C.c_int

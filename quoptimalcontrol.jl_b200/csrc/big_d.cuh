@@ -184,6 +184,7 @@ struct BigState {
   std::vector<int*> scan_tab;     // closed-system boundary scan: level l lists the chunk columns q*Cn + c with c >= 2^l
   int *bndW0 = nullptr, *bndU = nullptr, *bndOut = nullptr;   // chunk-boundary conjugations: slot of W_0, column of U_c, slot of W[start_{c+1}]
   int *bndS0 = nullptr, *bndEnd = nullptr, *bndCN = nullptr;  // general path, per (chain, chunk): slot 0, slot end_c, slot N
+  bool have_props = false;        // Pfinal / T hold the propagators and chunk totals of the last qoc_total_propagator call (one chain)
   PureState pure;                 // vector fast path for pure-state transfers on sparse closed systems (pure_state.cuh)
 };
 
@@ -359,7 +360,7 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
   const int M = d.M, K = d.K, D = d.D;
   const size_t dd = (size_t)D * D;
   int rc;
-  s->batch_c0 = -1; s->pure.batch_c0 = -1;
+  s->batch_c0 = -1; s->pure.batch_c0 = -1; s->have_props = false;
   auto rep = [&](double2* dst, const double* src, size_t per_member, bool sh) -> int {
     for (int k = 0; k < M; k++)
       if ((rc = big_upload_padded(s, dst + (size_t)k * per_member * s->DD, src + (sh ? 0 : (size_t)k * per_member * 2 * dd), per_member, err))) return rc;
@@ -410,6 +411,21 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
     BIG_CUDA(cudaMemcpy(s->coo_val, val.data(), val.size() * sizeof(double2), cudaMemcpyHostToDevice));
   }
   return pure_setup(s->pure, d, A, B, Xi, Xt, shared, s->herm != 0, err);
+}
+
+// Replace only the initial / target operators (slice-parallel multi-GPU: every evaluation brings new boundary operators,
+// drift and controls stay).  Propagators left by big_total_propagator stay valid.
+static inline int big_set_states(BigState* s, const double* Xi, const double* Xt, int shared, std::string& err) {
+  if (s->pure.active) { err = "qoc_set_states: the handle runs the pure-state vector path; create it with QOC_FLAG_NO_PURE_STATE"; return QOC_EUNSUPPORTED; }
+  const int M = s->d.M;
+  const size_t dd = (size_t)s->d.D * s->d.D;
+  int rc;
+  for (int k = 0; k < M; k++) {
+    if ((rc = big_upload_padded(s, s->Xi + (size_t)k * s->DD, Xi + ((shared & QOC_SHARED_XI) ? 0 : (size_t)k * 2 * dd), 1, err))) return rc;
+    if ((rc = big_upload_padded(s, s->Xt + (size_t)k * s->DD, Xt + ((shared & QOC_SHARED_XT) ? 0 : (size_t)k * 2 * dd), 1, err))) return rc;
+  }
+  s->batch_c0 = -1;       // the per-batch copies XiQ / XtQ are stale
+  return QOC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- launches
@@ -826,8 +842,15 @@ static int pure_eval(BigState* s, const double* x_dev, double* FG_dev, int want_
   return QOC_OK;
 }
 
+// reuse: skip the propagator and chunk-total phases and continue from what big_total_propagator left (same pulse, one chain)
 static inline int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
-                           std::string& err, qoc_stats& stats) {
+                           std::string& err, qoc_stats& stats, bool reuse = false) {
+  if (reuse) {
+    if (s->pure.active || !s->have_props || s->d.M * s->d.R != 1) {
+      err = "qoc_eval_continue: needs a dense-path handle with M = R = 1 and an immediately preceding qoc_total_propagator call";
+      return QOC_EINVAL;
+    }
+  } else s->have_props = false;
   if (s->pure.active) return pure_eval(s, x_dev, FG_dev, want_grad, wts_dev, st, err, stats);
   const qoc_desc& d = s->d;
   const int NK = d.N * d.K, total = d.M * d.R;
@@ -837,8 +860,10 @@ static inline int big_eval(BigState* s, const double* x_dev, double* FG_dev, int
   for (int c0 = 0; c0 < total; c0 += step) {
     const int nb = std::min(step, total - c0);
     if ((rc = big_set_batch(s, c0, nb, st, err))) return rc;
-    if ((rc = big_propagators_phase(s, nb, x_dev, st, err, stats))) return rc;
-    if ((rc = big_chunk_totals(s, nb, st, err, stats))) return rc;
+    if (!reuse) {
+      if ((rc = big_propagators_phase(s, nb, x_dev, st, err, stats))) return rc;
+      if ((rc = big_chunk_totals(s, nb, st, err, stats))) return rc;
+    }
     if (batched) { if ((rc = big_eval_batch_unitary(s, nb, st, err, stats))) return rc; }
     else if ((rc = big_eval_member(s, want_grad, st, err, stats))) return rc;
     big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev, s->tau_fom, s->gk, wts_dev, s->chain_member, s->chain_pulse, nb, NK, want_grad);
@@ -860,6 +885,7 @@ static int big_unpad(BigState* s, double2* dst, const double2* src, size_t count
 static inline int big_propagators(BigState* s, const double* x_dev, double2* out, int mode, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   int rc;
+  s->have_props = false;
   for (int c = 0; c < d.M * d.R; c++) {
     if ((rc = big_set_batch(s, c, 1, st, err))) return rc;
     const double2* src;
@@ -879,6 +905,7 @@ static inline int big_total_propagator(BigState* s, const double* x_dev, double2
   const qoc_desc& d = s->d;
   const size_t DD = s->DD;
   int rc;
+  s->have_props = false;
   for (int c = 0; c < d.M * d.R; c++) {
     if ((rc = big_set_batch(s, c, 1, st, err))) return rc;
     if ((rc = big_propagators_phase(s, 1, x_dev, st, err, stats))) return rc;
@@ -888,6 +915,7 @@ static inline int big_total_propagator(BigState* s, const double* x_dev, double2
     const double2* cur = Up + (size_t)(s->Cn - 1) * DD;
     if ((rc = big_unpad(s, out + (size_t)c * d.D * d.D, cur, 1, st, err))) return rc;
   }
+  s->have_props = d.M * d.R == 1;
   return QOC_OK;
 }
 

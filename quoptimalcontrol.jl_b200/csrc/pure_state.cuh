@@ -12,8 +12,9 @@
 // the same F and G to rounding; the arithmetic is NOT the 9 dense products per slice the roofline contract credits, so
 // bench.py reports this path separately from the contract figure.
 //
-// One CTA per (chain, direction): the whole time sweep of a chain is one kernel, vectors and the assembled H_t live in
-// shared memory, one __syncthreads per Taylor term.  Chains (members x pulses) are independent CTAs.
+// One CTA per (chain, direction): the whole time sweep of a chain is one kernel.  Every thread keeps its row's share of the
+// union sparsity pattern (columns, contributions, assembled entries of -+i dt H_t) in registers, shared memory holds the
+// ping-pong vector, one __syncthreads per Taylor term.  Chains (members x pulses) are independent CTAs.
 #pragma once
 #include <cuda_runtime.h>
 #include <string>

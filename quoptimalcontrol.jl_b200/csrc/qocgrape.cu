@@ -31,6 +31,7 @@ struct qoc_handle {
   double2 *storeP2 = nullptr, *stS = nullptr, *stC = nullptr, *totT = nullptr, *totTt = nullptr;
   double* tau = nullptr;
   int chunked = 0;                       // chunk-parallel fused mode (150..1500 chains)
+  bool big_reuse = false;                // qoc_eval_continue: big_eval continues from the propagators of qoc_total_propagator
   int chunked_closed = 0;                // >= 1500 chains: chunking (Cn = 4) only pays with the closed-system recursion
   int unitary_fast = 1;                  // closed-system conjugation kernel when the problem is Hermitian (QOC_UNITARY_FAST=0 disables)
   double2 *bS = nullptr, *bC = nullptr;
@@ -522,7 +523,7 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
 static int eval_device_on(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, cudaStream_t st) {
   h->st.launches_last_eval = 0;
   h->st.n_evals++;
-  if (h->path == 2) return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st);
+  if (h->path == 2) return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st, h->big_reuse);
   return eval_small(h, x_dev, FG_dev, want_gradient, st);
 }
 
@@ -599,6 +600,40 @@ extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
     if (F) F[r] = h->hout[r * row];
     if (G) memcpy(G + (size_t)r * h->NK, h->hout + r * row + 1, sizeof(double) * h->NK);
   }
+  return QOC_OK;
+}
+
+// Slice-parallel use (one rank per range of slices): new boundary operators per evaluation, drift and controls stay.
+extern "C" int qoc_set_states(qoc_handle* h, const double* Xi, const double* Xt, int shared_flags) {
+  if (!h) return QOC_EINVAL;
+  if (!Xi || !Xt) { h->err = "qoc_set_states: null pointer"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_set_states: qoc_set_system has not been called"; return QOC_EINVAL; }
+  if (h->path != 2) { h->err = "qoc_set_states: only implemented for D > 16 (tiled GEMM path)"; return QOC_EUNSUPPORTED; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return big_set_states(h->big, Xi, Xt, shared_flags, h->err);
+}
+
+// F (and G) for the pulse of the immediately preceding qoc_total_propagator call, reusing its propagators and chunk totals.
+extern "C" int qoc_eval_continue(qoc_handle* h, double* F, double* G) {
+  if (!h) return QOC_EINVAL;
+  if (!h->system_set) { h->err = "qoc_eval_continue: qoc_set_system has not been called"; return QOC_EINVAL; }
+  if (h->path != 2) { h->err = "qoc_eval_continue: only implemented for D > 16 (tiled GEMM path)"; return QOC_EUNSUPPORTED; }
+  const qoc_desc& d = h->d;
+  QOC_CUDA(h, cudaSetDevice(d.device));
+  QOC_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  h->big_reuse = true;
+  int rc = eval_device_on(h, h->x, h->out, G != nullptr, h->stream);
+  h->big_reuse = false;
+  if (rc != QOC_OK) return rc;
+  QOC_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  QOC_CUDA(h, copy_result_async(h, G != nullptr));
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  QOC_CUDA(h, cudaEventElapsedTime(&h->st.gpu_ms_last_eval, h->ev0, h->ev1));
+  const size_t row = (size_t)h->NK + 1;
+  if (F) F[0] = h->hout[0];
+  if (G) memcpy(G, h->hout + 1, sizeof(double) * h->NK);
+  (void)row;
   return QOC_OK;
 }
 

@@ -1,6 +1,11 @@
-"""Multi-GPU sharding of the ensemble: one process per GPU, members block-partitioned over
-ranks, one all-reduce(sum) of the weighted partial [F | G] per evaluation — the only collective.
-The serial member loop of the reference (/root/reference/src/solve.jl:166) is the axis that is sharded."""
+"""Multi-GPU sharding: one process per GPU.
+
+ShardedEnsembleEvaluator: ensemble members block-partitioned over ranks, one all-reduce(sum) of the weighted partial
+[F | G] per evaluation — the only collective.  The serial member loop of the reference
+(/root/reference/src/solve.jl:166) is the axis that is sharded.
+
+SliceParallelEvaluator: ONE large instance (M = 1), the time slices block-partitioned over ranks; the only exchange is
+an all-gather of one D x D range propagator per rank, plus the gather of the gradient blocks."""
 from __future__ import annotations
 
 import numpy as np
@@ -39,3 +44,74 @@ class ShardedEnsembleEvaluator:
             self.dist.all_reduce(t)          # sum over ranks
             fg = t.numpy()
         return float(fg[0]), fg[1:].reshape(K, N)
+
+
+
+class SliceParallelEvaluator:
+    """Slice-parallel evaluation of one problem (A, B, Xi, Xt) over the ranks of `dist`.
+
+    Rank r owns the slices [lo_r, hi_r) and a local evaluator for that range (N_r slices, duration T N_r / N).  Per call:
+      1. U_r = local.total_propagator(x[:, lo:hi])                 (propagators of the range stay on the device)
+      2. all-gather of the U_r                                      (the exchange: one D x D matrix per rank)
+      3. boundary operators of the range, with L = U_{r-1} ... U_0 and R = U_{n-1} ... U_{r+1}:
+           UnitaryGate:  S_lo = L Xi,     C_hi = R' Xt          (src/GRAPE.jl:226, :228 applied to whole ranges)
+           density:      S_lo = L Xi L',  C_hi = R' Xt R        (src/GRAPE.jl:245-249)
+      4. local.set_states(S_lo, C_hi); F, G_r = local.eval_continue()
+      5. all-gather of the gradient blocks.
+    Every rank's F is the full figure of merit (tr(S_t' C_t) does not depend on t) and G_r holds exactly the entries the
+    single-device evaluation produces for those slices, so the result equals GrapeEvaluator.eval on one device.
+
+    `make_local(n_slices, duration)` builds the local evaluator: a GrapeEvaluator with pure_state=False on a GPU; tests
+    inject a CPU stand-in with the same four methods to exercise the plumbing over gloo."""
+
+    def __init__(self, Xi, Xt, T, n_slices, unitary, make_local, dist=None):
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        if n_slices < self.world:
+            raise ValueError("SliceParallelEvaluator needs at least one slice per rank")
+        self.N, self.unitary = int(n_slices), bool(unitary)
+        self.Xi, self.Xt = np.asarray(Xi, dtype=np.complex128), np.asarray(Xt, dtype=np.complex128)
+        self.bounds = [shard_bounds(self.N, r, self.world) for r in range(self.world)]
+        self.lo, self.hi = self.bounds[self.rank]
+        self.local = make_local(self.hi - self.lo, float(T) * (self.hi - self.lo) / self.N)
+
+    def _all_gather(self, arr):
+        if self.dist is None or self.world == 1:
+            return [arr]
+        import torch
+        dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"       # NCCL moves device tensors only
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.float64).reshape(-1).copy()).to(dev)
+        sizes = None
+        if arr.ndim == 2 and arr.dtype == np.float64:        # gradient blocks: ranks own different numbers of slices
+            sizes = [(hi - lo) * arr.shape[0] for lo, hi in self.bounds]
+        if sizes is None:
+            out = [torch.empty_like(t) for _ in range(self.world)]
+            self.dist.all_gather(out, t)
+            return [o.cpu().numpy().view(arr.dtype).reshape(arr.shape) for o in out]
+        pad = max(sizes)
+        tp = torch.zeros(pad, dtype=torch.float64, device=dev)
+        tp[:t.numel()] = t
+        out = [torch.empty_like(tp) for _ in range(self.world)]
+        self.dist.all_gather(out, tp)
+        return [o.cpu().numpy()[:n].reshape(arr.shape[0], -1) for o, n in zip(out, sizes)]
+
+    def eval(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        K = x.shape[0]
+        U = self._all_gather(self.local.total_propagator(x[:, self.lo:self.hi]))
+        D = self.Xi.shape[0]
+        L = np.eye(D, dtype=np.complex128)
+        for r in range(self.rank):
+            L = U[r] @ L
+        Rm = np.eye(D, dtype=np.complex128)
+        for r in range(self.rank + 1, self.world):
+            Rm = U[r] @ Rm
+        if self.unitary:
+            S_lo, C_hi = L @ self.Xi, Rm.conj().T @ self.Xt
+        else:
+            S_lo, C_hi = L @ self.Xi @ L.conj().T, Rm.conj().T @ self.Xt @ Rm
+        self.local.set_states(S_lo, C_hi)
+        F, G_r = self.local.eval_continue()
+        blocks = self._all_gather(np.ascontiguousarray(G_r, dtype=np.float64).reshape(K, self.hi - self.lo))
+        return F, np.concatenate(blocks, axis=1)

@@ -118,6 +118,19 @@ class GrapeEvaluator:
         U = np.swapaxes(U, -1, -2)
         return U[0, 0].copy() if (self.R == 1 and self.M == 1) else U
 
+    def set_states(self, Xi, Xt):
+        """Replace the initial / target operators of a single-member handle (slice-parallel use, qoc_set_states)."""
+        xi = _colmajor([Xi], self.D)
+        xt = _colmajor([Xt], self.D)
+        self._check(self._lib.qoc_set_states(self._h, xi.ctypes.data, xt.ctypes.data, 0))
+
+    def eval_continue(self, want_grad=True):
+        """(F, G) for the pulse of the immediately preceding total_propagator() call, reusing its propagators."""
+        F = np.empty(1)
+        G = np.empty((self.N, self.K)) if want_grad else None
+        self._check(self._lib.qoc_eval_continue(self._h, F.ctypes.data, None if G is None else G.ctypes.data))
+        return float(F[0]), (None if G is None else np.ascontiguousarray(G.T))
+
     def propagators(self, x, what="propagator"):
         """pw_prop_save! / pw_ham_save! / pw_gen_save!: out[R, M, N, D, D] (squeezed for R = M = 1)."""
         mode = {"propagator": 0, "hamiltonian": 1, "generator": 2}[what]

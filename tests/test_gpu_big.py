@@ -250,3 +250,48 @@ def test_pure_state_path_without_controls(monkeypatch):
         path = ev.stats()["path"]
     Fo, _ = orc.fom_and_gradient_grape(A, [], np.zeros((0, 5)), 1.0, Xi, Xt, orc.STATE_TRANSFER)
     assert path in (2, 3) and abs(F - Fo) <= 1e-10 * max(1.0, abs(Fo))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# slice-range evaluation on one device: the C-ABI pieces of the slice-parallel multi-GPU mode
+@pytest.mark.parametrize("sys_name", ["state", "unitary", "coherence"])
+@pytest.mark.parametrize("gradient", ["first_order", "exact"])
+def test_set_states_and_eval_continue(sys_name, gradient):
+    """Two handles own the slice ranges [0, 5) and [5, 12) of one D = 40 problem (what two ranks would hold): range
+    propagators -> boundary operators -> qoc_set_states -> qoc_eval_continue reproduces the full evaluation."""
+    if gradient == "exact" and sys_name == "coherence":
+        pytest.skip("the reference defines no exact functional for CoherenceTransfer")
+    D, K, N, T, cut = 40, 2, 12, 1.1, 5
+    sys_type = SYS[sys_name]
+    A, B, Xi, Xt = random_system(D, K, seed=300 + len(sys_name), hermitian=(sys_name != "coherence"),
+                                 unitary_targets=(sys_name == "unitary"))
+    x = np.random.default_rng(11).uniform(-1, 1, (K, N))
+    I = np.eye(D, dtype=complex)
+    ranges = [(0, cut), (cut, N)]
+    evs = [qoc.GrapeEvaluator([(A, B, I, I)], T * (hi - lo) / N, hi - lo, sys_type, gradient=gradient, pure_state=False)
+           for lo, hi in ranges]
+    try:
+        U = [ev.total_propagator(x[:, lo:hi]) for ev, (lo, hi) in zip(evs, ranges)]
+        dagger = lambda m: m.conj().T
+        if sys_name == "unitary":
+            states = [(Xi, dagger(U[1]) @ Xt), (U[0] @ Xi, Xt)]
+        else:
+            states = [(Xi, dagger(U[1]) @ Xt @ U[1]), (U[0] @ Xi @ dagger(U[0]), Xt)]
+        Fs, Gs = [], []
+        for ev, (lo, hi), (s_lo, c_hi) in zip(evs, ranges, states):
+            ev.total_propagator(x[:, lo:hi])          # the call eval_continue continues from
+            ev.set_states(s_lo, c_hi)
+            F, G = ev.eval_continue()
+            Fs.append(F); Gs.append(G)
+        with pytest.raises(qoc._lib.QocError):
+            evs[0].eval(x[:, :cut]); evs[0].eval_continue()        # an ordinary eval in between invalidates the propagators
+    finally:
+        for ev in evs:
+            ev.close()
+    if gradient == "exact":
+        Fo, Go = orc.exact_fom_and_gradient(A, B, x, T, Xi, Xt, sys_type)
+    else:
+        Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, sys_type)
+    for F in Fs:
+        assert abs(F - Fo) <= 1e-10 * max(1.0, abs(Fo))
+    assert_parity(Fs[0], np.concatenate(Gs, axis=1), Fo, Go)

@@ -65,3 +65,50 @@ def test_oneshot_allreduce_two_gpus():
     for rank, errs in res:
         for ef, eg in errs:
             assert ef < 1e-10 and eg < 1e-8
+
+
+def _slice_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import quoptimalcontrol_jl_b200 as qoc
+    from oracle import grape_oracle as orc
+    from conftest import random_system
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    errs = []
+    for sys_type, name in [(orc.STATE_TRANSFER, "state"), (orc.UNITARY_GATE, "unitary"), (orc.COHERENCE_TRANSFER, "coherence")]:
+        D, K, N, T = 64, 2, 11, 0.9
+        A, B, Xi, Xt = random_system(D, K, seed=120 + sys_type, hermitian=(sys_type != orc.COHERENCE_TRANSFER),
+                                     unitary_targets=(sys_type == orc.UNITARY_GATE))
+        x = np.random.default_rng(7).uniform(-1, 1, (K, N))
+        I = np.eye(D, dtype=complex)
+        ev = qoc.SliceParallelEvaluator(
+            Xi, Xt, T, N, sys_type == orc.UNITARY_GATE,
+            lambda n, dur: qoc.GrapeEvaluator([(A, B, I, I)], dur, n, sys_type, device=rank, pure_state=False), dist=dist)
+        for _ in range(2):                       # second call: states replaced again on the same handle
+            F, G = ev.eval(x)
+        Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, sys_type)
+        errs.append((name, abs(F - Fo) / max(1.0, abs(Fo)), float(np.max(np.abs(G - Go)) / max(np.max(np.abs(Go)), 1e-6))))
+        ev.local.close()
+    q.put((rank, errs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_slice_parallel_two_gpus():
+    """One D = 64 instance, its 11 slices split over two GPUs (qoc_total_propagator -> exchange -> qoc_set_states ->
+    qoc_eval_continue): same F and G as the single-device evaluation / the oracle."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slice_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        for name, ef, eg in errs:
+            assert ef < 1e-10 and eg < 1e-8, (rank, name, ef, eg)
