@@ -64,8 +64,9 @@ class SliceParallelEvaluator:
     `make_local(n_slices, duration)` builds the local evaluator: a GrapeEvaluator with pure_state=False on a GPU; tests
     inject a CPU stand-in with the same four methods to exercise the plumbing over gloo."""
 
-    def __init__(self, Xi, Xt, T, n_slices, unitary, make_local, dist=None):
+    def __init__(self, Xi, Xt, T, n_slices, unitary, make_local, dist=None, device=None):
         self.dist = dist
+        self.device = device          # torch device for the small boundary products (None: numpy on the host)
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
         if n_slices < self.world:
@@ -96,21 +97,31 @@ class SliceParallelEvaluator:
         self.dist.all_gather(out, tp)
         return [o.cpu().numpy()[:n].reshape(arr.shape[0], -1) for o, n in zip(out, sizes)]
 
+    def _boundary_operators(self, U):
+        """State before and costate after this rank's range from the gathered range propagators (a handful of D x D
+        products: plumbing around the path, done with torch on the device when one is given, else numpy)."""
+        if self.device is not None:
+            import torch
+            to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            U, Xi, Xt = [to(u) for u in U], to(self.Xi), to(self.Xt)
+            mm, dag, back = torch.matmul, (lambda m: m.conj().transpose(-1, -2)), (lambda m: m.cpu().numpy())
+        else:
+            U, Xi, Xt = list(U), self.Xi, self.Xt
+            mm, dag, back = np.matmul, (lambda m: m.conj().T), (lambda m: m)
+        L = Rm = None
+        for r in range(self.rank):
+            L = U[r] if L is None else mm(U[r], L)
+        for r in range(self.rank + 1, self.world):
+            Rm = U[r] if Rm is None else mm(U[r], Rm)
+        S_lo = Xi if L is None else (mm(L, Xi) if self.unitary else mm(mm(L, Xi), dag(L)))
+        C_hi = Xt if Rm is None else (mm(dag(Rm), Xt) if self.unitary else mm(mm(dag(Rm), Xt), Rm))
+        return back(S_lo), back(C_hi)
+
     def eval(self, x):
         x = np.asarray(x, dtype=np.float64)
         K = x.shape[0]
         U = self._all_gather(self.local.total_propagator(x[:, self.lo:self.hi]))
-        D = self.Xi.shape[0]
-        L = np.eye(D, dtype=np.complex128)
-        for r in range(self.rank):
-            L = U[r] @ L
-        Rm = np.eye(D, dtype=np.complex128)
-        for r in range(self.rank + 1, self.world):
-            Rm = U[r] @ Rm
-        if self.unitary:
-            S_lo, C_hi = L @ self.Xi, Rm.conj().T @ self.Xt
-        else:
-            S_lo, C_hi = L @ self.Xi @ L.conj().T, Rm.conj().T @ self.Xt @ Rm
+        S_lo, C_hi = self._boundary_operators(U)
         self.local.set_states(S_lo, C_hi)
         F, G_r = self.local.eval_continue()
         blocks = self._all_gather(np.ascontiguousarray(G_r, dtype=np.float64).reshape(K, self.hi - self.lo))

@@ -85,7 +85,8 @@ def _slice_worker(rank, world, port, q):
         I = np.eye(D, dtype=complex)
         ev = qoc.SliceParallelEvaluator(
             Xi, Xt, T, N, sys_type == orc.UNITARY_GATE,
-            lambda n, dur: qoc.GrapeEvaluator([(A, B, I, I)], dur, n, sys_type, device=rank, pure_state=False), dist=dist)
+            lambda n, dur: qoc.GrapeEvaluator([(A, B, I, I)], dur, n, sys_type, device=rank, pure_state=False), dist=dist,
+            device=torch.device("cuda", rank) if sys_type != orc.STATE_TRANSFER else None)     # both host and device boundary products
         for _ in range(2):                       # second call: states replaced again on the same handle
             F, G = ev.eval(x)
         Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, sys_type)
