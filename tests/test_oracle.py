@@ -133,3 +133,81 @@ def test_julia_exp_rung_for_baseline_configs():
         for i in range(cfg["N"]):
             deg, prods, s = orc.julia_exp_rung(-1j * dt * orc.pw_ham(A, B, cfg["x"], i))
             assert (deg, prods, s) == (5, 3, 0), (cfg["name"], i, deg)
+
+
+# ---- algebraic identities the CUDA paths rely on, pinned against the line-by-line oracle on the CPU -------------------
+def _closed_system(D, K, N, seed):
+    rng = np.random.default_rng(seed)
+    herm = lambda: (lambda Z: (Z + Z.conj().T) / 2)(rng.normal(size=(D, D)) + 1j * rng.normal(size=(D, D)))
+    return herm(), [herm() for _ in range(K)], rng.uniform(-1, 1, (K, N)), rng
+
+
+def test_closed_system_conjugation_recursion():
+    """Hermitian drift and controls: W_t = S_t C_t' - C_t' S_t = U_t W_0 U_t' with U_t = P_{t-1} ... P_0, so one forward
+    recursion replaces both sweeps; the gradient from it equals the oracle's."""
+    D, K, N, T = 5, 2, 9, 1.3
+    A, B, x, rng = _closed_system(D, K, N, 1)
+    rho = lambda: (lambda Z: Z @ Z.conj().T)(rng.normal(size=(D, D)) + 1j * rng.normal(size=(D, D)))
+    Xi, Xt = rho(), rho()
+    dt = T / N
+    P = orc.pw_prop_save(A, B, x, dt)
+    UN = np.eye(D, dtype=complex)
+    for p in P:
+        UN = p @ UN
+    C0 = UN.conj().T @ Xt @ UN
+    W = Xi @ C0.conj().T - C0.conj().T @ Xi
+    G = np.zeros((K, N))
+    for t in range(N):
+        for c in range(K):
+            G[c, t] = np.real(1j * dt * np.trace(B[c] @ W))
+        W = P[t] @ W @ P[t].conj().T
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert np.max(np.abs(G - Go)) < 1e-12 * max(1.0, np.max(np.abs(Go)))
+    tau = np.trace(C0.conj().T @ Xi)
+    assert abs((1 - abs(tau / D) ** 2) - Fo) < 1e-12 * max(1.0, abs(Fo))
+
+
+def test_pure_state_vector_identities():
+    """Xi = psi psi', Xt = phi phi' on a closed system: g[c,t] = -2 dt Im(conj(o_t) chi_t' B_c psi_t), o_t = chi_t' psi_t,
+    fom = 1 - |o|^4 / D^2 (the formulas of csrc/pure_state.cuh) reproduce the oracle."""
+    D, K, N, T = 6, 3, 8, 0.9
+    A, B, x, rng = _closed_system(D, K, N, 2)
+    ket = lambda: (lambda v: v / np.linalg.norm(v))(rng.normal(size=D) + 1j * rng.normal(size=D))
+    psi0, phi = ket(), ket()
+    Xi, Xt = np.outer(psi0, psi0.conj()), np.outer(phi, phi.conj())
+    dt = T / N
+    P = orc.pw_prop_save(A, B, x, dt)
+    psi = [psi0]
+    for p in P:
+        psi.append(p @ psi[-1])
+    chi = [None] * (N + 1)
+    chi[N] = phi
+    for t in range(N - 1, -1, -1):
+        chi[t] = P[t].conj().T @ chi[t + 1]
+    G = np.zeros((K, N))
+    for t in range(N):
+        o = np.vdot(chi[t], psi[t])
+        for c in range(K):
+            G[c, t] = -2 * dt * np.imag(np.conj(o) * np.vdot(chi[t], B[c] @ psi[t]))
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.STATE_TRANSFER)
+    assert np.max(np.abs(G - Go)) < 1e-13 * max(1.0, np.max(np.abs(Go)))
+    o = np.vdot(chi[N - 1], psi[N - 1])
+    assert abs((1 - abs(o) ** 4 / D ** 2) - Fo) < 1e-13
+
+
+def test_slice_range_boundary_operators():
+    """Slice-parallel algebra: a range evaluated with S_lo = L Xi L', C_hi = R' Xt R as its initial / target
+    operators returns the full figure of merit and exactly its slices' gradient entries."""
+    D, K, N, T, cut = 4, 2, 10, 1.1, 4
+    A, B, x, rng = _closed_system(D, K, N, 3)
+    A = A + 0.05j * rng.normal(size=(D, D))                      # not Hermitian: the identity does not need unitarity
+    rho = lambda: (lambda Z: Z @ Z.conj().T)(rng.normal(size=(D, D)) + 1j * rng.normal(size=(D, D)))
+    Xi, Xt = rho(), rho()
+    I = np.eye(D, dtype=complex)
+    dt = T / N
+    U0, U1 = orc.pw_evolve(A, B, x[:, :cut], dt, I), orc.pw_evolve(A, B, x[:, cut:], dt, I)
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, orc.COHERENCE_TRANSFER)
+    F0, G0 = orc.fom_and_gradient_grape(A, B, x[:, :cut], dt * cut, Xi, U1.conj().T @ Xt @ U1, orc.COHERENCE_TRANSFER)
+    F1, G1 = orc.fom_and_gradient_grape(A, B, x[:, cut:], dt * (N - cut), U0 @ Xi @ U0.conj().T, Xt, orc.COHERENCE_TRANSFER)
+    assert abs(F0 - Fo) < 1e-12 * max(1.0, abs(Fo)) and abs(F1 - Fo) < 1e-12 * max(1.0, abs(Fo))
+    assert np.max(np.abs(np.concatenate([G0, G1], axis=1) - Go)) < 1e-12 * max(1.0, np.max(np.abs(Go)))
