@@ -137,9 +137,11 @@ def run_reference(args, cfg, rank):
     dt = (time.perf_counter() - t0) / args.steps
     value = 1.0 / (dt * scale)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True,
+            "scaling": "strong" if M > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": cfg["name"], "gradient": cfg["gradient"]},
+            "config": {"workload": cfg["name"], "D": D, "K": int(cfg["x"].shape[0]), "N": int(cfg["N"]), "M": M, "pulses_per_step": 1,
+                       "gradient": cfg["gradient"], "parallelism": f"host CPU, {threads} threads (rank 0 only)"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind_fn == "c" and M > 1 else (threads if kind_fn == "numpy" else 1),
                              "kind": "port", "sample": sample + ("; C restatement + OpenMP over members" if kind_fn == "c" else "; numpy/OpenBLAS restatement")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
