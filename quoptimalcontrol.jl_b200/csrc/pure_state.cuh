@@ -337,7 +337,7 @@ static inline int pure_setup(PureState& ps, const qoc_desc& d, const double* A, 
     if (lpt > 12 || !pure_kernel_for(lpt, CWt)) continue;
     if (threads <= pure_max_threads(lpt, CWt)) { tpr_log2 = tl; LPT = lpt; nthreads = threads; }
   }
-  if (tpr_log2 < 0) return QOC_OK;
+  if (tpr_log2 < 0 || K > nthreads) return QOC_OK;      // the sweep stages the K amplitudes of a slice with one thread each
   const int TPR = 1 << tpr_log2;
   ps.smem = 2 * (size_t)D * 16 + 32 * 8 + (size_t)(K + 1) * 8;
   ps.D = D; ps.K = K; ps.N = N; ps.M = M; ps.Lu = Lu; ps.Cw = Cw; ps.CWt = CWt; ps.LPT = LPT; ps.tpr_log2 = tpr_log2; ps.nthreads = nthreads;

@@ -70,3 +70,34 @@ def test_bench_reference_arm_prints_one_json_line():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["config"]["workload"].startswith("cfg1")
+
+
+def test_slice_parallel_evaluator_single_process():
+    """SliceParallelEvaluator without a process group owns all slices: set_states receives Xi / Xt unchanged and the result
+    is the local evaluator's (CPU stand-in built on the oracle; the multi-rank algebra is in tests/test_dist_gloo.py)."""
+    import numpy as np
+    from oracle import grape_oracle as orc
+    from conftest import random_system
+    import quoptimalcontrol_jl_b200 as qoc
+
+    class Local:
+        def __init__(self, A, B, n, dur):
+            self.A, self.B, self.N, self.T = A, B, n, dur
+        def total_propagator(self, x):
+            self.x = x
+            return orc.pw_evolve(self.A, self.B, x, self.T / self.N, np.eye(self.A.shape[0], dtype=complex))
+        def set_states(self, Xi, Xt):
+            self.Xi, self.Xt = Xi, Xt
+        def eval_continue(self):
+            return orc.fom_and_gradient_grape(self.A, self.B, self.x, self.T, self.Xi, self.Xt, orc.STATE_TRANSFER)
+
+    A, B, Xi, Xt = random_system(4, 2, seed=1)
+    x = np.random.default_rng(0).uniform(-1, 1, (2, 5))
+    ev = qoc.SliceParallelEvaluator(Xi, Xt, 1.0, 5, False, lambda n, dur: Local(A, B, n, dur))
+    assert (ev.lo, ev.hi, ev.world) == (0, 5, 1)
+    F, G = ev.eval(x)
+    Fo, Go = orc.fom_and_gradient_grape(A, B, x, 1.0, Xi, Xt, orc.STATE_TRANSFER)
+    assert abs(F - Fo) < 1e-14 and np.max(np.abs(G - Go)) < 1e-14 and np.array_equal(ev.local.Xi, Xi)
+    import pytest
+    with pytest.raises(ValueError):
+        qoc.SliceParallelEvaluator(Xi, Xt, 1.0, 0, False, lambda n, dur: None)
