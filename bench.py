@@ -3,11 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4|cfg1|cfg2|cfg3|cfg5] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+    python bench.py --gpus N --single-process        (one process, one multi-device handle: qoc_desc.n_devices = N)
 
 One "step" = one evaluation of the (F, G, x) closure (solve.jl:75-100 / :164-196) for the whole workload: all
-ensemble members weighted and summed (and, for N > 1, one all-reduce of [F|G] over NCCL).  Default workload:
-BASELINE.json configs[3], the 4096-member robust ensemble (the config the 1/2/4/8-GPU metric is quoted on); its
-members are sharded over the ranks (strong scaling: total work fixed).  Prints ONE JSON line on rank 0.
+ensemble members weighted and summed (and, for N > 1, one all-reduce of [F|G]).  Default workload: BASELINE.json
+configs[3], the 4096-member robust ensemble (the config the 1/2/4/8-GPU metric is quoted on); its members are sharded
+over the ranks (strong scaling: total work fixed).  Prints ONE JSON line on rank 0.
+
+The parity object compares the TIMED handle's own output (the device buffer left by the last timed step, i.e. after the
+all-reduce when N > 1, and the last end-to-end call's host result) with the CPU restatement over ALL members.
+At N = 1 the line also carries `secondary`: the other BASELINE configs (cfg5 dense D = 256 path with full-size parity
+against tests/golden/cfg5_full*.npz; cfg1-3 at one pulse and at a saturating multi-start batch).
 """
 import argparse
 import json
@@ -26,126 +32,274 @@ METRIC = "GRAPE fidelity+gradient evals/sec"
 UNIT = "evals/s"
 FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "fp64_peak.json")
 TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic.json")
-
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 _OUT = sys.stdout
+DEFAULT_PULSES = {"cfg4": 1, "cfg5": 1, "cfg1": 65536, "cfg2": 4096, "cfg3": 1024}
 
 
 def build_config(name):
     import quoptimalcontrol_jl_b200 as qoc
     c = qoc.configs
-    if name == "cfg4":
-        return c.config4()
-    if name == "cfg1":
-        return c.config1()
-    if name == "cfg2":
-        return c.config2()
-    if name == "cfg3":
-        return c.config3()
-    if name == "cfg5":
-        return c.config5()
-    raise SystemExit(f"unknown config {name}")
+    try:
+        return {"cfg1": c.config1, "cfg2": c.config2, "cfg3": c.config3, "cfg4": c.config4, "cfg5": c.config5}[name]()
+    except KeyError:
+        raise SystemExit(f"unknown config {name}")
 
 
-DEFAULT_PULSES = {"cfg4": 1, "cfg5": 1, "cfg1": 65536, "cfg2": 4096, "cfg3": 1024}
+def config_dict(cfg, pulses_per_step):
+    """The workload description, identical in both arms (no prose that differs between them)."""
+    A, B = cfg["members"][0][0], cfg["members"][0][1]
+    D, K, N, M = A.shape[0], len(B), int(cfg["N"]), len(cfg["members"])
+    store_gb = M * pulses_per_step * N * D * D * 16 / 1e9
+    return {"workload": cfg["name"], "D": D, "K": K, "N": N, "M": M, "pulses_per_step": int(pulses_per_step),
+            "gradient": cfg["gradient"],
+            "l2": "no flush: every step streams its per-slice propagator store (%.2f GB) >> 126 MB L2" % store_gb
+            if store_gb > 0.5 else "no flush: working set %.3f GB, L2-resident between steps (stated, latency-bound case)" % store_gb}
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in a thread every ~2 ms
+    (nvidia-smi -lms as the fallback).  Started well before the timed loop so that short timed regions still get rows."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.stop_flag, self.proc, self.nvml = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.maxclk = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.nvml = None
+            try:
+                q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "20"],
+                                             stdout=subprocess.PIPE, text=True)
+                self.th = threading.Thread(target=self._read, daemon=True)
+                self.th.start()
+            except OSError:
+                self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = int(reasons_fn(self.h))
+                self.rows.append((time.perf_counter(), sm, self.maxclk, pw, {v for k, v in self.BITS.items() if rs & k}))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        rows = [r for (t, r) in self.rows if (t0 is None or t >= t0) and (t1 is None or t <= t1)] or [r for _, r in self.rows]
-        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            f = [s.strip() for s in r.split(",")]
+        for line in self.proc.stdout:
+            f = [s.strip() for s in line.split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]),
+                                  {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+
+    def stop(self, t0, t1):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        rows = inside or [r for r in self.rows if t0 - 0.25 <= r[0] <= t1 + 0.05]      # nearest rows under the same load
+        if not rows:
             return None
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        reasons = set().union(*[r[4] for r in rows])
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "power_w_max": float(max(r[3] for r in rows)), "samples": len(rows), "samples_in_timed_region": len(inside),
+                "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------ oracle side
+def oracle_eval(cfg, threads, members=None, wts=None, x=None, N=None):
+    """(F, G, seconds, description) of the CPU restatement on the given workload (default: the whole config)."""
+    from oracle import c_oracle, grape_oracle
+    members = cfg["members"] if members is None else members
+    wts = cfg["wts"] if wts is None else wts
+    x = cfg["x"] if x is None else x
+    N = cfg["N"] if N is None else N
+    T = cfg["T"] * N / cfg["N"]
+    D = members[0][0].shape[0]
+    w = wts if wts is not None else np.ones(len(members))
+    t0 = time.perf_counter()
+    if cfg["gradient"] == "exact":
+        F, G = grape_oracle.ensemble_exact(members, w, x, T, cfg["sys_type"])
+        how, cores = "numpy restatement of the ADGRAPE functional with augmented-matrix derivatives", 1
+    elif D > 16:
+        F, G = grape_oracle.ensemble_fom_and_gradient(members, w, x, T, cfg["sys_type"])
+        how, cores = "numpy/OpenBLAS restatement of the reference loop order (3K GEMMs per slice), all BLAS threads", threads
+    else:
+        nt = threads if len(members) > 1 else 1
+        F, G = c_oracle.eval_ensemble(members, wts, x, T, cfg["sys_type"], 0, nt)
+        how = "C restatement of the reference loop order" + (", OpenMP over members (the Julia reference is serial)" if nt > 1 else ", 1 thread (the reference is serial)")
+        cores = nt
+    return F, G, time.perf_counter() - t0, how, cores
+
+
+def parity_of(Fg, Gg, Fo, Go, checked_on, floor=1e-300):
+    Gg, Go = np.asarray(Gg), np.asarray(Go)
+    scale = max(float(np.max(np.abs(Go))), floor)
+    out = {"fom_rel_err": float(abs(Fg - Fo) / max(1.0, abs(Fo))), "grad_rel_err_inf": float(np.max(np.abs(Gg - Go)) / scale),
+           "grad_inf_norm": float(np.max(np.abs(Go))), "checked_on": checked_on, "tolerance": "1e-10 fom / 1e-8 gradient (inf-norm relative)"}
+    out["ok"] = bool(out["fom_rel_err"] <= 1e-10 and out["grad_rel_err_inf"] <= 1e-8)
+    return out
 
 
 def run_reference(args, cfg, rank):
-    """--impl reference: the reference's own CPU implementation of the path, restated in C (oracle/grape_oracle.c,
-    Julia being unavailable), all host threads, on a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path, restated in C / numpy (Julia being
+    unavailable), all host threads.  Every step evaluates the WHOLE workload (all members, all slices) except for cfg5,
+    where a step is a bounded sample of slices (stated)."""
     if rank != 0:
         return
-    from oracle import c_oracle, grape_oracle
-    members, wts = cfg["members"], cfg["wts"]
-    M = len(members)
-    D = members[0][0].shape[0]
+    M = len(cfg["members"])
+    D = cfg["members"][0][0].shape[0]
     threads = os.cpu_count() or 1
     if D > 16:
-        kind_fn = "numpy"
+        ns = min(cfg["N"], 8)
+        kw = dict(x=cfg["x"][:, :ns], N=ns)
+        scale, sample = cfg["N"] / ns, f"{ns} of {cfg['N']} slices per step, scaled x{cfg['N'] / ns:g}"
     else:
-        kind_fn = "c"
-    # bounded sample: members for ensembles, slices for single long chains (cost is linear in both)
-    if M > 1:
-        ms = min(M, max(threads, 64))
-        sample_members, sample_w, x, N = members[:ms], (wts[:ms] if wts is not None else None), cfg["x"], cfg["N"]
-        scale = M / ms
-        sample = f"{ms} of {M} members (all {cfg['N']} slices), scaled x{scale:g}"
-    else:
-        ns = min(cfg["N"], 200 if D <= 16 else 8)
-        sample_members, sample_w, x, N = members, wts, cfg["x"][:, :ns], ns
-        scale = cfg["N"] / ns
-        sample = f"{ns} of {cfg['N']} slices, scaled x{scale:g}"
-    T = cfg["T"] * N / cfg["N"]
-
-    def step():
-        if kind_fn == "c":
-            if cfg["gradient"] == "exact":
-                return grape_oracle.ensemble_exact(sample_members, sample_w if sample_w is not None else [1.0], x, T, cfg["sys_type"])
-            return c_oracle.eval_ensemble(sample_members, sample_w, x, T, cfg["sys_type"], 0, threads)
-        return grape_oracle.ensemble_fom_and_gradient(sample_members, sample_w if sample_w is not None else [1.0], x, T, cfg["sys_type"])
-
+        kw, scale, sample = {}, 1.0, f"all {M} members, all {cfg['N']} slices per step (no extrapolation)"
+    how, cores = "", 1
     for _ in range(args.warmup):
-        step()
+        _, _, _, how, cores = oracle_eval(cfg, threads, **kw)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
-    value = 1.0 / (dt * scale)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True,
-            "scaling": "strong" if M > 1 else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": cfg["name"], "D": D, "K": int(cfg["x"].shape[0]), "N": int(cfg["N"]), "M": M, "pulses_per_step": 1,
-                       "gradient": cfg["gradient"], "parallelism": f"host CPU, {threads} threads (rank 0 only)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind_fn == "c" and M > 1 else (threads if kind_fn == "numpy" else 1),
-                             "kind": "port", "sample": sample + ("; C restatement + OpenMP over members" if kind_fn == "c" else "; numpy/OpenBLAS restatement")},
+        _, _, _, how, cores = oracle_eval(cfg, threads, **kw)
+    dt = (time.perf_counter() - t0) / args.steps * scale
+    value = 1.0 / dt
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong" if M > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config_dict(cfg, 1),
+            "parallelism": f"host CPU, {cores} threads (rank 0 only)",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample + "; " + how},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_OUT, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU side
+def fp64_peak():
+    peak, src = 37.1, "fallback constant (tools/microbench/fp64_pipes.cu DMMA burst)"
+    if os.path.exists(FP64_PEAK_FILE):
+        with open(FP64_PEAK_FILE) as f:
+            pj = json.load(f)
+        peak, src = float(pj["fp64_dmma_tflops"]), pj["source"]
+    return peak, src + " — builder-measured: MEASURED_PEAKS.json has no FP64 entry (64 FP64 MAC/clk/SM x 148 SM x 1.965 GHz x 2 = 37.2)"
+
+
+def products_per_slice(cfg, path, K):
+    import quoptimalcontrol_jl_b200 as qoc
+    unitary = cfg["sys_type"] == qoc._lib.UNITARY_GATE
+    credited = (3 * (1 + 2 * K) if cfg["gradient"] == "exact" else 3) + (2 if unitary else 4) + (1 if unitary else 2)
+    executed = None
+    if cfg["gradient"] != "exact":
+        m = cfg["members"][0]
+        herm = np.array_equal(m[0], m[0].conj().T) and all(np.array_equal(b, b.conj().T) for b in m[1])
+        if path == 2:
+            executed = 7 if herm else (4 + 1 + (2 if unitary else 4) + (1 if unitary else 2))
+        elif path == 1:
+            executed = 6 if herm else credited         # closed-system conjugation recursion: 3 expm + 1 total + 2 sweep
+    return credited, executed
+
+
+def time_device(ev, x_dev, fg_dev, stream, steps, warmup, torch):
+    for _ in range(warmup):
+        ev.eval_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
+    torch.cuda.synchronize()
+    ev.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ev.eval_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def secondary_config(name, R, qoc, torch, dev, local_rank, peak, threads, steps=5):
+    """One of the other BASELINE configs on this GPU: device-resident and end-to-end timing, roofline, full-size parity."""
+    cfg = build_config(name)
+    K, N = cfg["x"].shape
+    D = cfg["members"][0][0].shape[0]
+    rng = np.random.default_rng(4321)
+    xs = np.concatenate([cfg["x"][None], rng.uniform(-1, 1, (R - 1, K, N))]) if R > 1 else cfg["x"][None]
+    out = {"config": config_dict(cfg, R)}
+    stream = torch.cuda.current_stream()
+    with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"], wts=cfg["wts"], gradient=cfg["gradient"], n_pulses=R,
+                            device=local_rank, pure_state=False) as ev:
+        x_dev = torch.from_numpy(np.ascontiguousarray(np.swapaxes(xs, 1, 2))).to(dev)
+        fg_dev = torch.zeros((R, N * K + 1), dtype=torch.float64, device=dev)
+        ms = time_device(ev, x_dev, fg_dev, stream, steps, 3, torch)
+        st = ev.stats()
+        xin = xs if R > 1 else xs[0]
+        ev.eval(xin)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            Fg, Gg = ev.eval(xin)
+        e2e_s = (time.perf_counter() - t0) / steps
+        fg = fg_dev.cpu().numpy()
+        credited, executed = products_per_slice(cfg, st["path"], K)
+        flops = qoc.configs.alg_flops(cfg) * R
+        ratio = min(1.0, executed / credited) if executed else 1.0
+        ach = flops / (ms * 1e-3) / 1e12
+        out.update({"ms_per_step": ms, "value": R / (ms * 1e-3), "unit": UNIT,
+                    "e2e": {"value": R / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(R * N * K * 8), "d2h_bytes_per_step": int(R * (N * K + 1) * 8)},
+                    "gpu_launches_per_step": int(st["launches_last_eval"]),
+                    "roofline": {"bound": "tensor", "achieved": ach * ratio, "peak": peak, "unit": "TFLOP/s", "frac": ach * ratio / peak,
+                                 "achieved_credited": ach, "frac_credited": ach / peak,
+                                 "products_per_slice": {"credited": credited, "executed": executed}, "alg_flops_per_step": flops,
+                                 "note": "whole step timed (CUDA events), all launches"}})
+        # ---- full-size parity of the timed handle's own output
+        if name == "cfg5":
+            z = np.load(os.path.join(GOLDEN, "cfg5_full.npz"))
+            Go = np.ascontiguousarray(z["G"])
+            Gd = fg[0, 1:].reshape(N, K).T
+            out["parity"] = parity_of(fg[0, 0], Gd, float(z["F"]), Go, "full size (2000 slices) vs tests/golden/cfg5_full.npz, device buffer of the timed handle")
+            out["parity"]["e2e_result"] = parity_of(Fg, Gg, float(z["F"]), Go, "last qoc_eval result")["ok"]
+            zd = np.load(os.path.join(GOLDEN, "cfg5_full_dense.npz"))
+            sys.path.insert(0, GOLDEN)
+            from make_golden_cfg5 import dense_states
+            ev.set_states(*dense_states(D))
+            Fd, Gdn = ev.eval(cfg["x"])
+            out["parity_dense_states"] = parity_of(Fd, Gdn, float(zd["F"]), zd["G"], "full size, seeded dense Xi/Xt vs tests/golden/cfg5_full_dense.npz (same handle via qoc_set_states)")
+        else:
+            worst = None
+            for r in sorted({0, R - 1}):
+                Fo, Go, _, how, _ = oracle_eval(cfg, threads, x=xs[r])
+                p = parity_of(fg[r, 0], fg[r, 1:].reshape(N, K).T, Fo, Go, f"full size, pulses {sorted({0, R - 1})} of {R}; {how}; device buffer of the timed handle")
+                pe = parity_of(Fg[r] if R > 1 else Fg, Gg[r] if R > 1 else Gg, Fo, Go, "")
+                p["e2e_result"] = pe["ok"]
+                if worst is None or p["grad_rel_err_inf"] > worst["grad_rel_err_inf"]:
+                    worst = p
+            out["parity"] = worst
+    if name == "cfg5":      # the separate pure-state vector path (not the contract arithmetic): timing + full-size parity
+        with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"], device=local_rank) as evp:
+            if evp.stats()["path"] == 3:
+                for _ in range(3):
+                    Fp, Gp = evp.eval(cfg["x"])
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    evp.eval(cfg["x"])
+                tp = (time.perf_counter() - t0) / steps
+                z = np.load(os.path.join(GOLDEN, "cfg5_full.npz"))
+                out["pure_state_path"] = {"value": 1.0 / tp, "unit": UNIT, "ms_per_step": tp * 1e3, "timed": "end to end through qoc_eval (host buffers)",
+                                          "gpu_launches_per_step": int(evp.stats()["launches_last_eval"]),
+                                          "parity": parity_of(Fp, Gp, float(z["F"]), z["G"], "full size vs tests/golden/cfg5_full.npz"),
+                                          "note": "state-vector sweep for pure-state transfers on sparse closed systems (QOC_FLAG_NO_PURE_STATE unset): "
+                                                  "same F and G to rounding, O(nnz) work per slice, no FP64-roofline fraction is claimed for it"}
+    return out
 
 
 def main():
@@ -156,7 +310,10 @@ def main():
     ap.add_argument("--config", default="cfg4")
     ap.add_argument("--pulses", type=int, default=0, help="multi-start pulses per step (0 = config default)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU restatement (no cpu_baseline, no parity)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (N = 1 default run only)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process drives --gpus devices through ONE multi-device handle (qoc_desc.n_devices), no torchrun")
     ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
                     help="N > 1: fused one-shot all-reduce over NVLink peer memory (default) or torch.distributed NCCL")
     args = ap.parse_args()
@@ -185,30 +342,38 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    single_proc = args.single_process and world == 1 and args.gpus > 1
+    n_gpus = args.gpus if single_proc else world
 
     members, wts = cfg["members"], cfg["wts"]
     M = len(members)
     K, N = cfg["x"].shape
+    D = members[0][0].shape[0]
     R = args.pulses or DEFAULT_PULSES[args.config]
     sharded = M > 1
-    if sharded:   # ensemble members sharded over ranks, one all-reduce of [F|G] per evaluation
+    if sharded and not single_proc:   # ensemble members sharded over ranks, one all-reduce of [F|G] per evaluation
         lo, hi = rank * M // world, (rank + 1) * M // world
         my_members, my_wts, my_R = members[lo:hi], wts[lo:hi], R
-        parallelism = f"ensemble-sharded x{world} + allreduce" if world > 1 else "single GPU"
+        parallelism = f"ensemble-sharded x{world}, one process per GPU" if world > 1 else "single GPU"
+    elif single_proc:
+        if not sharded:
+            raise SystemExit("--single-process shards ensemble members: use an ensemble config (cfg4)")
+        my_members, my_wts, my_R = members, wts, R
+        parallelism = f"ensemble-sharded x{n_gpus} inside ONE process (multi-device handle, qoc_desc.n_devices)"
     else:         # M = 1: replicas over independent multi-start pulses, no collective
         my_members, my_wts, my_R = members, wts, R
         parallelism = f"multi-start replicas x{world}, no collective" if world > 1 else "single GPU"
     rng = np.random.default_rng(1234 + (0 if sharded else rank))
     xs = np.concatenate([cfg["x"][None], rng.uniform(-1, 1, (my_R - 1, K, N))]) if my_R > 1 else cfg["x"][None]
+    xin = xs if my_R > 1 else xs[0]
 
     # pure_state=False: the contract figure is the dense 9-products-per-slice evaluation; the pure-state
-    # vector path changes the algorithmic FLOP count and is reported separately below ("pure_state_path")
-    ev = qoc.GrapeEvaluator(my_members, cfg["T"], N, cfg["sys_type"], wts=my_wts, gradient=cfg["gradient"],
-                            n_pulses=my_R, device=local_rank, pure_state=False)
+    # vector path changes the algorithmic FLOP count and is reported separately ("pure_state_path")
+    ev = qoc.GrapeEvaluator(my_members, cfg["T"], N, cfg["sys_type"], wts=my_wts, gradient=cfg["gradient"], n_pulses=my_R,
+                            device=local_rank, pure_state=False, devices=list(range(n_gpus)) if single_proc else None)
     x_host = torch.from_numpy(np.ascontiguousarray(np.swapaxes(xs, 1, 2))).pin_memory()     # [R][N][K]
     x_dev = x_host.to(dev)
     fg_dev = torch.zeros((my_R, N * K + 1), dtype=torch.float64, device=dev)
-    fg_host = torch.zeros((my_R, N * K + 1), dtype=torch.float64).pin_memory()
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
@@ -219,33 +384,39 @@ def main():
             dist.all_gather_object(handles, ev.comm_export())
             ev.comm_connect(world, rank, handles)
             ok = 1
-        except Exception as exc:                   # e.g. CUDA IPC not permitted on this box
-            ok, why = 0, str(exc)
+        except Exception:                          # e.g. CUDA IPC not permitted on this box
+            ok = 0
         t = torch.tensor([ok], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)   # all ranks must agree on the collective they use
         if int(t.item()) == 1:
-            parallelism += " (one-shot NVLink peer-memory all-reduce kernel)"
+            parallelism += " + one-shot NVLink peer-memory all-reduce fused with the member reduction (graph-replayed)"
         else:
             oneshot = False
-            parallelism += " (NCCL all-reduce; one-shot unavailable)"
+            parallelism += " + NCCL all-reduce (one-shot unavailable)"
     elif world > 1 and sharded:
-        parallelism += " (NCCL all-reduce)"
+        parallelism += " + NCCL all-reduce"
+
+    last = {}
 
     def step_device():
-        if oneshot:
+        if single_proc:                            # a multi-device handle has the host-buffer entry only
+            last["F"], last["G"] = ev.eval(xin)
+        elif oneshot:
             ev.eval_allreduce_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
-            return
-        ev.eval_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
-        if world > 1 and sharded:
-            dist.all_reduce(fg_dev)
+        else:
+            ev.eval_device(x_dev.data_ptr(), fg_dev.data_ptr(), True, stream.cuda_stream)
+            if world > 1 and sharded:
+                dist.all_reduce(fg_dev)
 
-    def step_e2e():
-        if world == 1:
-            return ev.eval(xs if my_R > 1 else xs[0])            # C-ABI call with host buffers (H2D + kernels + D2H)
-        x_dev.copy_(x_host, non_blocking=True)
-        step_device()
-        fg_host.copy_(fg_dev, non_blocking=True)
-        torch.cuda.synchronize()
+    def step_e2e():                                # the public host-buffer call: H2D + kernels (+ all-reduce) + D2H inside
+        if oneshot:
+            last["F"], last["G"] = ev.eval_allreduce(xin)
+        elif world > 1 and sharded:
+            x_dev.copy_(x_host, non_blocking=True)
+            step_device()
+            last["fg"] = fg_dev.cpu()
+        else:
+            last["F"], last["G"] = ev.eval(xin)
 
     def barrier():
         torch.cuda.synchronize()
@@ -254,7 +425,21 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None     # started early: nvidia-smi needs ~0.1 s to come up
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # untimed pre-spin of ~0.4 s: brings the clocks up and lets the sampler start.  The step count is agreed between the
+    # ranks (every rank must issue the same sequence of all-reduce calls).
+    t_spin = time.perf_counter()
+    for _ in range(4):
+        step_device()
+    torch.cuda.synchronize()
+    n_spin = int(min(2000, max(4, 0.4 / max((time.perf_counter() - t_spin) / 4, 1e-5))))
+    if world > 1:
+        t = torch.tensor([n_spin], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_spin = int(t.item())
+    for _ in range(n_spin):
+        step_device()
+    barrier()
     for _ in range(args.warmup):
         step_device()
     barrier()
@@ -268,14 +453,15 @@ def main():
     barrier()
     t_end = time.perf_counter()
     clocks = sampler.stop(t_start, t_end) if sampler else None
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = (t_end - t_start) * 1e3 / args.steps if single_proc else e0.elapsed_time(e1) / args.steps
     st = ev.stats()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    evals_per_step = R if sharded else R * world
+    evals_per_step = R if (sharded or single_proc) else R * world
     value = evals_per_step / (ms * 1e-3)
+    timed_fg = None if single_proc else fg_dev.cpu().numpy()       # what the LAST TIMED step left on the device
 
     # ---- end-to-end timing through the public API (host buffers, copies inside the timed region) ----
     for _ in range(2):
@@ -290,8 +476,9 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": evals_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(my_R * N * K * 8),
-           "d2h_bytes_per_step": int(my_R * (N * K + 1) * 8)}
+    e2e = {"value": evals_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(my_R * N * K * 8) * (n_gpus if single_proc else 1),
+           "d2h_bytes_per_step": int(my_R * (N * K + 1) * 8),
+           "api": "qoc_eval_allreduce (host buffers, one CUDA-graph launch per rank)" if oneshot else "qoc_eval (host buffers)"}
 
     if rank != 0:
         if world > 1:
@@ -301,16 +488,12 @@ def main():
 
     # ---- roofline of the dominant kernel ----
     flops_total = qoc.configs.alg_flops(cfg) * R                    # algorithmic FLOPs of one step, whole job
-    flops_rank = flops_total / world if sharded else flops_total    # per launch of this rank's kernel
-    peak, peak_src = 37.1, "fallback constant (tools/microbench/fp64_pipes.cu DMMA burst)"
-    if os.path.exists(FP64_PEAK_FILE):
-        with open(FP64_PEAK_FILE) as f:
-            pj = json.load(f)
-        peak, peak_src = float(pj["fp64_dmma_tflops"]), pj["source"]
-    k_ms = st["main_kernel_ms_avg"] or ms
+    flops_rank = flops_total / n_gpus if sharded else flops_total   # per launch of one GPU's kernels
+    peak, peak_src = fp64_peak()
+    k_ms = (st["main_kernel_ms_avg"] or ms) if not single_proc else ms
     if st["path"] == 1:
         kernel_name = ("warp-resident FP64 DMMA chain kernels (chunk_expm + boundary + sweep, or chain_kernel): %d launches per "
-                       "evaluation incl. the two reduce passes; events around the chain-kernel group" % st["launches_last_eval"])
+                       "evaluation incl. the reduction; events around the chain-kernel group" % st["launches_last_eval"])
     else:
         kernel_name = "zgemm_dmma_kernel x %d launches per step (whole step timed: GEMMs are >98%% of it)" % st["launches_last_eval"]
     achieved = flops_rank / (k_ms * 1e-3) / 1e12
@@ -318,130 +501,70 @@ def main():
     if os.path.exists(TRAFFIC_FILE):
         with open(TRAFFIC_FILE) as f:
             traffic = json.load(f).get(args.config)
-    # products actually executed per slice (the closed-system conjugation recursion needs fewer than the credited count)
-    unitary_sys = cfg["sys_type"] == qoc._lib.UNITARY_GATE
-    credited = (3 * (1 + 2 * K) if cfg["gradient"] == "exact" else 3) + (2 if unitary_sys else 4) + (1 if unitary_sys else 2)
-    executed = None
-    if st["path"] == 2 and cfg["gradient"] != "exact":
-        herm = all(np.array_equal(m[0], m[0].conj().T) and all(np.array_equal(b, b.conj().T) for b in m[1]) for m in members[:1])
-        executed = 7 if herm else (4 + 1 + (2 if unitary_sys else 4) + (1 if unitary_sys else 2))
-    elif st["path"] == 1 and cfg["gradient"] != "exact":
-        executed = credited
-    # `achieved` / `frac` count the products the kernels actually execute (never more than the credited algorithmic count):
-    # the closed-system recursion needs 7 of the 9 credited products per slice, and crediting 9 would put cfg5 above the
-    # pipe's peak.  The credited convention is kept alongside as achieved_credited / frac_credited.
+    credited, executed = products_per_slice(cfg, st["path"], K)
+    # `achieved` / `frac` count the products the kernels actually execute (never more than the credited algorithmic count)
     ratio = min(1.0, executed / credited) if executed else 1.0
     roofline = {"bound": "tensor", "achieved": achieved * ratio, "peak": peak, "unit": "TFLOP/s", "frac": achieved * ratio / peak,
                 "achieved_credited": achieved, "frac_credited": achieved / peak,
                 "products_per_slice": {"credited": credited, "executed": executed},
                 "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
                 "kernel_samples": st["main_kernel_samples"], "alg_flops_per_launch": flops_rank,
-                "executed_flops_per_launch": flops_rank * ratio,
-                "peak_source": peak_src + " — MEASURED_PEAKS.json has no FP64 entry"}
+                "executed_flops_per_launch": flops_rank * ratio, "peak_source": peak_src}
 
-    # ---- CPU baseline (reference restated in C, all host threads, bounded sample) + parity gate ----
+    # ---- CPU restatement over the WHOLE workload: parity of the timed handle's own output (+ cpu_baseline at N = 1) ----
     cpu_baseline, parity = None, None
-    if world == 1 and not args.no_cpu_baseline:
-        from oracle import c_oracle, grape_oracle
+    if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        D = members[0][0].shape[0]
-        if M > 1:  # noqa
-            ms_n = min(M, max(2 * threads, 64))
-            sm, sw = members[:ms_n], wts[:ms_n]
-            t0 = time.perf_counter()
-            Fo, Go = c_oracle.eval_ensemble(sm, sw, cfg["x"], cfg["T"], cfg["sys_type"], 0, threads)
-            tc = time.perf_counter() - t0
-            cpu_baseline = {"value": 1.0 / (tc * M / ms_n), "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": f"{ms_n} of {M} members, all {N} slices, C restatement of the reference loop order with OpenMP over members (the Julia reference is serial); scaled x{M / ms_n:g}"}
-            # the parity sample has few chains: force the execution strategy of the timed run (fused, one warp per chain)
-            saved = {k: os.environ.get(k) for k in ("QOC_PHASED", "QOC_CHUNKED")}
-            os.environ["QOC_PHASED"] = "0"; os.environ["QOC_CHUNKED"] = "0"
-            try:
-                with qoc.GrapeEvaluator(sm, cfg["T"], N, cfg["sys_type"], wts=sw, gradient=cfg["gradient"], device=local_rank) as ev2:
-                    Fg, Gg = ev2.eval(cfg["x"])
-            finally:
-                for k, v in saved.items():
-                    if v is None:
-                        os.environ.pop(k, None)
-                    else:
-                        os.environ[k] = v
+        if D > 16:
+            z = np.load(os.path.join(GOLDEN, "cfg5_full.npz")) if args.config == "cfg5" else None
+            if z is not None and timed_fg is not None:
+                parity = parity_of(timed_fg[0, 0], timed_fg[0, 1:].reshape(N, K).T, float(z["F"]), z["G"],
+                                   "full size vs tests/golden/cfg5_full.npz, device buffer of the timed handle")
+            ns = 8
+            _, _, tc, how, cores = oracle_eval(cfg, threads, x=cfg["x"][:, :ns], N=ns)
+            cpu_baseline = {"value": 1.0 / (tc * N / ns), "unit": UNIT, "cores": cores, "kind": "port", "sample": f"{ns} of {N} slices, {how}; scaled x{N / ns:g}"}
         else:
-            ns = min(N, 100 if D <= 16 else 16)
-            xsmp = cfg["x"][:, :ns]
-            Ts = cfg["T"] * ns / N
-            t0 = time.perf_counter()
-            pm = members
-            if D > 16:
-                # a 16-slice prefix cannot move |0..0> towards |1..1>: F = 1 and G ~ 1e-29 would make the parity figure
-                # pure rounding noise.  The sample keeps operators, pulse and dt but uses seeded dense states.
-                prng = np.random.default_rng(99)
-                def dens():
-                    Z = prng.standard_normal((D, D)) + 1j * prng.standard_normal((D, D))
-                    Z = Z @ Z.conj().T
-                    return Z / np.trace(Z).real
-                pm = [(members[0][0], members[0][1], dens(), dens())]
-                Fo, Go = grape_oracle.fom_and_gradient_grape(*pm[0][:2], xsmp, Ts, *pm[0][2:], cfg["sys_type"])
-                how = "numpy/OpenBLAS restatement of the reference loop order (3K GEMMs per slice), all BLAS threads; parity on seeded dense random initial/target states"
-            elif cfg["gradient"] == "exact":
-                Fo, Go = grape_oracle.exact_fom_and_gradient(*members[0][:2], xsmp, Ts, *members[0][2:], cfg["sys_type"])
-                how = "numpy restatement of the ADGRAPE functional with augmented-matrix derivatives"
-            else:
-                Fo, Go = c_oracle.eval_ensemble(members, None, xsmp, Ts, cfg["sys_type"], 0, 1)
-                how = "C restatement of the reference loop order, 1 thread (the reference is serial)"
-            tc = time.perf_counter() - t0
-            cpu_baseline = {"value": 1.0 / (tc * N / ns), "unit": UNIT, "cores": threads if D > 16 else 1, "kind": "port",
-                            "sample": f"{ns} of {N} slices, {how}; scaled x{N / ns:g}"}
-            with qoc.GrapeEvaluator(pm, Ts, ns, cfg["sys_type"], gradient=cfg["gradient"], device=local_rank) as ev2:
-                Fg, Gg = ev2.eval(xsmp)
-        parity = {"fom_rel_err": abs(Fg - Fo) / max(1.0, abs(Fo)),
-                  "grad_rel_err_inf": float(np.max(np.abs(Gg - Go)) / max(np.max(np.abs(Go)), 1e-6)),
-                  "grad_inf_norm": float(np.max(np.abs(Go))),
-                  "checked_on": cpu_baseline["sample"].split(",")[0], "tolerance": "1e-10 fom / 1e-8 gradient"}
+            Fo, Go, tc, how, cores = oracle_eval(cfg, threads)
+            where = f"all {M} members x {N} slices" if M > 1 else f"full size ({N} slices)"
+            if timed_fg is not None:
+                parity = parity_of(timed_fg[0, 0], timed_fg[0, 1:].reshape(N, K).T, Fo, Go,
+                                   f"{where}: device buffer left by the last TIMED step" + (f" (after the {world}-rank all-reduce)" if world > 1 else "") + f"; {how}")
+            if "F" in last:
+                Fl, Gl = (last["F"][0], last["G"][0]) if my_R > 1 else (last["F"], last["G"])
+                pe = parity_of(Fl, Gl, Fo, Go, f"{where}: host result of the last end-to-end call; {how}")
+                if parity is None:
+                    parity = pe
+                else:
+                    parity["e2e_result"] = {k: pe[k] for k in ("fom_rel_err", "grad_rel_err_inf", "ok")}
+            if world == 1 and not single_proc:
+                cpu_baseline = {"value": 1.0 / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{where}, one evaluation (no extrapolation); {how}"}
 
-    # ---- separate figure: pure-state vector path (same F, G; O(nnz) per slice; not the contract arithmetic) ----
-    pure = None
-    D = members[0][0].shape[0]
-    if world == 1 and D > 16 and cfg["gradient"] != "exact":
-        with qoc.GrapeEvaluator(my_members, cfg["T"], N, cfg["sys_type"], wts=my_wts, n_pulses=my_R, device=local_rank) as evp:
-            if evp.stats()["path"] == 3:
-                xin = xs if my_R > 1 else xs[0]
-                for _ in range(3):
-                    evp.eval(xin)
-                t0 = time.perf_counter()
-                for _ in range(args.steps):
-                    evp.eval(xin)
-                tp = (time.perf_counter() - t0) / args.steps
-                pure = {"value": R / tp, "unit": UNIT, "ms_per_step": tp * 1e3, "timed": "end to end through qoc_eval (host buffers)",
-                        "gpu_launches_per_step": int(evp.stats()["launches_last_eval"]),
-                        "note": "state-vector sweep for pure-state transfers on sparse closed systems (QOC_FLAG_NO_PURE_STATE unset): "
-                                "same F and G to rounding, O(nnz) work per slice, so no FP64-roofline fraction is claimed for it"}
-        if pure is not None and not args.no_cpu_baseline:
-            from oracle import grape_oracle
-            ns = min(N, 16)
-            prng = np.random.default_rng(98)
-            def ket():
-                v = prng.standard_normal(D) + 1j * prng.standard_normal(D)
-                v /= np.linalg.norm(v)
-                return np.outer(v, v.conj())
-            pmem = (members[0][0], members[0][1], ket(), ket())
-            Fo, Go = grape_oracle.fom_and_gradient_grape(*pmem[:2], cfg["x"][:, :ns], cfg["T"] * ns / N, *pmem[2:], cfg["sys_type"])
-            with qoc.GrapeEvaluator([pmem], cfg["T"] * ns / N, ns, cfg["sys_type"], device=local_rank) as evq:
-                Fg, Gg = evq.eval(cfg["x"][:, :ns])
-                assert evq.stats()["path"] == 3
-            pure["parity"] = {"fom_rel_err": abs(Fg - Fo) / max(1.0, abs(Fo)),
-                              "grad_rel_err_inf": float(np.max(np.abs(Gg - Go)) / max(np.max(np.abs(Go)), 1e-6)),
-                              "grad_inf_norm": float(np.max(np.abs(Go))), "checked_on": f"{ns} of {N} slices, seeded random pure states"}
+    # ---- the other BASELINE configs (N = 1, default workload only) ----
+    secondary = None
+    if world == 1 and not single_proc and args.config == "cfg4" and not args.no_secondary:
+        ev.close()
+        del x_dev, fg_dev
+        torch.cuda.empty_cache()
+        secondary = {}
+        threads = os.cpu_count() or 1
+        for name, r in (("cfg5", 1), ("cfg1", 1), ("cfg1", 65536), ("cfg2", 1), ("cfg2", 4096), ("cfg3", 1), ("cfg3", 1024)):
+            key = name if r == 1 else f"{name}_batch{r}"
+            try:
+                secondary[key] = secondary_config(name, r, qoc, torch, dev, local_rank, peak, threads)
+            except Exception as exc:   # a secondary figure must never take the headline down with it
+                secondary[key] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "D": D, "K": K, "N": N, "M": M, "pulses_per_step": evals_per_step,
-                       "gradient": cfg["gradient"], "parallelism": parallelism,
-                       "l2": "no flush: every step writes and re-reads its per-slice propagator (and state) stores, %.2f GB of workspace >> 126 MB L2" % (st["workspace_bytes"] / 1e9)},
+            "dtype": "f64", "data": "synthetic", "config": config_dict(cfg, evals_per_step), "parallelism": parallelism,
             "e2e": e2e, "gpu_launches": int(st["launches_last_eval"]) * args.steps, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity}
-    if pure is not None:
-        line["pure_state_path"] = pure
+    if single_proc:
+        line["timing_note"] = "single-process multi-device handle: `value` is timed through qoc_eval with host buffers (wall clock, sync per step); it has no device-pointer entry"
+    if secondary is not None:
+        line["secondary"] = secondary
     print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()

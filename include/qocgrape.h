@@ -14,6 +14,8 @@
  *   - every function returns a status (0 = QOC_OK); no exception crosses the boundary;
  *   - the library copies inputs during the call and never retains host pointers;
  *   - a handle is used by one thread at a time; different handles are independent;
+ *   - a handle created with n_devices > 1 shards the ensemble members over several GPUs inside ONE process
+ *     (single-process multi-device: one qoc_eval call drives all of them, see qoc_desc.n_devices);
  *   - there is NO CPU fallback: without a CUDA device or for unsupported shapes an error is returned;
  *   - for D > 16 qoc_eval_device synchronises its stream once per evaluation (a 4-byte read of the scaling power).
  */
@@ -56,6 +58,8 @@ extern "C" {
 #define QOC_SHARED_XI 4
 #define QOC_SHARED_XT 8
 
+#define QOC_MAX_DEVICES 16
+
 typedef struct qoc_handle qoc_handle;
 
 typedef struct qoc_desc {
@@ -72,6 +76,14 @@ typedef struct qoc_desc {
   double expm_theta; /* scaling threshold of the degree-8 Taylor exponential; <= 0 selects the default
                         (0.0694: truncation error below 2^-53) */
   int flags;         /* QOC_FLAG_* bits, 0 = defaults */
+  /* Single-process multi-device ensembles (SURVEY.md 8b "Threading", 8e): with n_devices > 1 the M members are
+   * block-partitioned over device_ids[0 .. n_devices) (member k -> device k * n_devices / M, like the serial member loop
+   * src/solve.jl:166 cut into contiguous blocks); qoc_set_system uploads each block to its device, qoc_eval launches all
+   * blocks concurrently from the calling thread (one CUDA graph spanning the devices) and device_ids[0] sums the weighted
+   * partial [F|G] rows in fixed device order over NVLink peer memory before the single D2H copy.  `device` is ignored
+   * then.  An ordinal may be repeated (several shards on one device: useful for testing on a single-GPU box).  n_devices <= 1 keeps the single-device behaviour (and a zero-initialised tail keeps old callers valid). */
+  int n_devices;
+  int device_ids[QOC_MAX_DEVICES];
 } qoc_desc;
 
 typedef struct qoc_stats {
@@ -105,12 +117,20 @@ int qoc_set_system(qoc_handle* h, const double* A, const double* B, const double
 /* One fidelity+gradient evaluation per pulse: the body of the Optim.only_fg! closure
  * (src/solve.jl:75-100 single problem, :164-196 ensemble) = _fom_and_gradient_GRAPE! (src/GRAPE.jl:25-96)
  * over all members, weighted and summed.
- *   x [R][N*K] host;  F [R] or NULL;  G [R][N*K] or NULL (value-only evaluation skips the backward sweep). */
+ *   x [R][N*K] host;  F [R] or NULL;  G [R][N*K] or NULL (value-only evaluation skips the backward sweep).
+ * With G == NULL and R > 1 this is the batched fidelity-only call for gradient-free callers: one call evaluates a
+ * whole Nelder-Mead simplex / dCRAB candidate set (src/dCRAB.jl:52-70 evaluates them one user_func call at a time). */
 int qoc_eval(qoc_handle* h, const double* x, double* F, double* G);
+
+/* Optional control-amplitude / control-variation penalties added to every evaluation (the PenaltyFunctionals C3 and C4
+ * of src/cost_functions.jl:29-39, weighted):  F += w_amp * sum(x.^2) + w_var * sum(diff(x, dims = 2).^2) and G gets the
+ * matching derivative; applied once per pulse after the ensemble reduction (and after the all-reduce / device sum).
+ * Both weights 0 (the default) disables the extra kernel. */
+int qoc_set_penalty(qoc_handle* h, double w_amp, double w_var);
 
 /* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the CUDA default
  * stream, as everywhere in the CUDA runtime): x_dev [R][N*K];  FG_dev [R][1 + N*K] with F first, then G.  Lets one-process-per-GPU callers
- * all-reduce FG_dev (NCCL) without a host round trip. */
+ * all-reduce FG_dev (NCCL) without a host round trip.  With want_gradient == 0 the G columns of FG_dev are written as 0. */
 int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);
 
 /* pw_evolve (src/timeevolution.jl:28-39) with U0 = I:  U [R][M][D*D] = P_N ... P_1. */
@@ -138,12 +158,18 @@ int qoc_eval_continue(qoc_handle* h, double* F, double* G);
  * all_gather_object, MPI, a file).
  *   qoc_comm_export   allocate this rank's exchange buffer and return its IPC handle
  *   qoc_comm_connect  open the peers' buffers; handles = [world][QOC_IPC_HANDLE_BYTES], own entry included
- *   qoc_eval_allreduce_device   like qoc_eval_device, but FG_dev receives the sum over all ranks */
+ *   qoc_eval_allreduce_device   like qoc_eval_device, but FG_dev receives the sum over all ranks
+ *   qoc_eval_allreduce          like qoc_eval (HOST buffers; every rank passes the same x and receives the summed F, G):
+ *                               H2D, kernels, the all-reduce and D2H are one CUDA-graph launch per call
+ * The member reduction's second pass is folded into the all-reduce kernel, which keeps its epoch counter in device memory
+ * (so the whole sequence is graph-replayable).  All calls of a handle must be issued in the same order on every rank;
+ * qoc_comm_connect may be called once per handle. */
 #define QOC_IPC_HANDLE_BYTES 64
 #define QOC_MAX_RANKS 16
 int qoc_comm_export(qoc_handle* h, unsigned char* handle /* [QOC_IPC_HANDLE_BYTES] */);
 int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsigned char* handles);
 int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);
+int qoc_eval_allreduce(qoc_handle* h, const double* x, double* F, double* G);
 
 /* ---- the caller of the path: L-BFGS inside the library ---------------------------------------
  * Replaces `Optim.optimize(Optim.only_fg!(topt), guess, LBFGS(), optim_options)` (src/solve.jl:138, :244) for a

@@ -12,17 +12,19 @@ GRAD_FIRST_ORDER, GRAD_EXACT = 0, 1
 REF_INPLACE, REF_STATIC = 0, 1
 SHARED_A, SHARED_B, SHARED_XI, SHARED_XT = 1, 2, 4, 8
 IPC_HANDLE_BYTES = 64
+MAX_DEVICES = 16
 
 EXPORTS = ["qoc_version", "qoc_create", "qoc_destroy", "qoc_set_system", "qoc_eval", "qoc_eval_device",
            "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error",
            "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device", "qoc_minimize_lbfgs",
-           "qoc_set_states", "qoc_eval_continue"]
+           "qoc_set_states", "qoc_eval_continue", "qoc_eval_allreduce", "qoc_set_penalty"]
 
 
 class QocDesc(C.Structure):
     _fields_ = [("sys_type", C.c_int), ("D", C.c_int), ("K", C.c_int), ("N", C.c_int), ("M", C.c_int),
                 ("R", C.c_int), ("T", C.c_double), ("gradient", C.c_int), ("convention", C.c_int),
-                ("device", C.c_int), ("expm_theta", C.c_double), ("flags", C.c_int)]
+                ("device", C.c_int), ("expm_theta", C.c_double), ("flags", C.c_int),
+                ("n_devices", C.c_int), ("device_ids", C.c_int * MAX_DEVICES)]
 
 
 class QocStats(C.Structure):
@@ -75,6 +77,8 @@ def load():
     lib.qoc_comm_export.argtypes = [vp, vp]
     lib.qoc_comm_connect.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.qoc_eval_allreduce_device.argtypes = [vp, vp, vp, C.c_int, vp]
+    lib.qoc_eval_allreduce.argtypes = [vp, vp, vp, vp]
+    lib.qoc_set_penalty.argtypes = [vp, C.c_double, C.c_double]
     lib.qoc_set_states.argtypes = [vp, vp, vp, C.c_int]
     lib.qoc_eval_continue.argtypes = [vp, vp, vp]
     for name in EXPORTS:

@@ -20,7 +20,8 @@
 #include "../../include/qocgrape.h"
 #include "zgemm_dmma.cuh"
 #include "pure_state.cuh"
-#include "small_d.cuh"      // reduce_members_pass1/2
+#include "params.h"       // launch_reduce_pass1/2
+#include "big_api.h"
 
 namespace qoc {
 
@@ -157,7 +158,7 @@ struct BigState {
   // Chains (pulse r, member k) are evaluated Bc at a time: chain q of a batch owns slots [q*(N+1), (q+1)*(N+1)) of every
   // per-slice buffer and chunks [q*Cn, (q+1)*Cn), so all launches simply get a Bc times larger batch dimension.
   int Bc = 1, tabw = 1, CnMax = 1;
-  long long ws_tables = 0;
+  long long ws_tables = 0, ws_coo = 0;
   int batch_c0 = -1, batch_nb = 0;                      // batch currently described on the device (reset by set_system)
   int *chain_member = nullptr, *chain_pulse = nullptr, *chain_coo = nullptr;   // device [Bc]
   double2 *XiQ = nullptr, *XtQ = nullptr;                                     // per-chain copies of Xi, Xt for the batch
@@ -197,10 +198,10 @@ template <class T> static int big_alloc(BigState* s, T** p, size_t n, std::strin
   s->ws += (long long)(n * sizeof(T));
   return QOC_OK;
 }
-static inline long long big_workspace(BigState* s) { return s ? s->ws + s->pure.ws : 0; }
+long long big_workspace(BigState* s) { return s ? s->ws + s->pure.ws : 0; }
 
 static inline void big_free_tables(BigState* s);
-static inline void big_destroy(BigState* s) {
+void big_destroy(BigState* s) {
   if (!s) return;
   void* ptrs[] = {s->chain_member, s->chain_pulse, s->chain_coo, s->XiQ, s->XtQ, s->A, s->B, s->Xi, s->Xt, s->Q, s->T, s->tmpF, s->tmpB,
                   s->s_dev, s->norms, s->tau_fom, s->gk, s->coo_ptr, s->coo_idx, s->coo_val};
@@ -293,7 +294,7 @@ static int big_build_chunks(BigState* s, int Cn, std::string& err) {
   return QOC_OK;
 }
 
-static inline int big_create(BigState** out, const qoc_desc& d, std::string& err, long long& ws_total) {
+int big_create(BigState** out, const qoc_desc& d, std::string& err, long long& ws_total) {
   BigState* s = new BigState();
   *out = s;
   s->d = d;
@@ -355,7 +356,7 @@ static int big_upload_padded(BigState* s, double2* dst, const double* src, size_
   return QOC_OK;
 }
 
-static inline int big_set_system(BigState* s, const double* A, const double* B, const double* Xi, const double* Xt, int shared, std::string& err) {
+int big_set_system(BigState* s, const double* A, const double* B, const double* Xi, const double* Xt, int shared, std::string& err) {
   const qoc_desc& d = s->d;
   const int M = d.M, K = d.K, D = d.D;
   const size_t dd = (size_t)D * D;
@@ -404,7 +405,10 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
   }
   for (void* p : {(void*)s->coo_ptr, (void*)s->coo_idx, (void*)s->coo_val}) if (p) cudaFree(p);
   s->coo_ptr = nullptr; s->coo_idx = nullptr; s->coo_val = nullptr;
+  s->ws -= s->ws_coo;                      // a repeated qoc_set_system replaces the lists: keep workspace_bytes honest
+  const long long ws_before = s->ws;
   if ((rc = big_alloc(s, &s->coo_ptr, ptr.size(), err)) || (rc = big_alloc(s, &s->coo_idx, idx.size(), err)) || (rc = big_alloc(s, &s->coo_val, val.size(), err))) return rc;
+  s->ws_coo = s->ws - ws_before;
   BIG_CUDA(cudaMemcpy(s->coo_ptr, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
   if (!idx.empty()) {
     BIG_CUDA(cudaMemcpy(s->coo_idx, idx.data(), idx.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -415,7 +419,7 @@ static inline int big_set_system(BigState* s, const double* A, const double* B, 
 
 // Replace only the initial / target operators (slice-parallel multi-GPU: every evaluation brings new boundary operators,
 // drift and controls stay).  Propagators left by big_total_propagator stay valid.
-static inline int big_set_states(BigState* s, const double* Xi, const double* Xt, int shared, std::string& err) {
+int big_set_states(BigState* s, const double* Xi, const double* Xt, int shared, std::string& err) {
   if (s->pure.active) { err = "qoc_set_states: the handle runs the pure-state vector path; create it with QOC_FLAG_NO_PURE_STATE"; return QOC_EUNSUPPORTED; }
   const int M = s->d.M;
   const size_t dd = (size_t)s->d.D * s->d.D;
@@ -826,13 +830,12 @@ static int pure_eval(BigState* s, const double* x_dev, double* FG_dev, int want_
     pure_grad_kernel<<<dim3(gp.want_grad ? d.N : 1, nb), 256, (size_t)2 * d.D * sizeof(double2), st>>>(gp);
     BIG_COUNT();
     if (nb == total) {       // every chain in one batch (chain = r * M + k): deterministic two-pass weighted member reduction
-      dim3 g1((unsigned)(((NK + 1 + 255) / 256) * (long)d.R), ps.red_nchunks);
-      reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? ps.g : nullptr, ps.fomc, wts_dev, ps.red_nchunks == 1 ? FG_dev : ps.part, M, NK,
-                                               ps.red_chunk, ps.red_nchunks);
-      BIG_COUNT();
+      BIG_CUDA(launch_reduce_pass1(want_grad ? ps.g : nullptr, ps.fomc, wts_dev, ps.red_nchunks == 1 ? FG_dev : ps.part, M, NK, d.R,
+                                   ps.red_chunk, ps.red_nchunks, st));
+      stats.n_launches++; stats.launches_last_eval++;
       if (ps.red_nchunks > 1) {
-        reduce_members_pass2<<<(unsigned)(((NK + 1 + 31) / 32) * (long)d.R), 32 * RED_LANES, 0, st>>>(ps.part, FG_dev, NK, ps.red_nchunks);
-        BIG_COUNT();
+        BIG_CUDA(launch_reduce_pass2(ps.part, FG_dev, NK, d.R, ps.red_nchunks, st));
+        stats.n_launches++; stats.launches_last_eval++;
       }
     } else {
       big_accumulate_kernel<<<(NK + 1 + 255) / 256, 256, 0, st>>>(FG_dev, ps.tau_fom, ps.g, wts_dev, ps.member, ps.pulse, nb, NK, want_grad);
@@ -843,8 +846,8 @@ static int pure_eval(BigState* s, const double* x_dev, double* FG_dev, int want_
 }
 
 // reuse: skip the propagator and chunk-total phases and continue from what big_total_propagator left (same pulse, one chain)
-static inline int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
-                           std::string& err, qoc_stats& stats, bool reuse = false) {
+int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, const double* wts_dev, cudaStream_t st,
+                           std::string& err, qoc_stats& stats, bool reuse) {
   if (reuse) {
     if (s->pure.active || !s->have_props || s->d.M * s->d.R != 1) {
       err = "qoc_eval_continue: needs a dense-path handle with M = R = 1 and an immediately preceding qoc_total_propagator call";
@@ -882,7 +885,7 @@ static int big_unpad(BigState* s, double2* dst, const double2* src, size_t count
   return QOC_OK;
 }
 
-static inline int big_propagators(BigState* s, const double* x_dev, double2* out, int mode, cudaStream_t st, std::string& err, qoc_stats& stats) {
+int big_propagators(BigState* s, const double* x_dev, double2* out, int mode, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   int rc;
   s->have_props = false;
@@ -901,7 +904,7 @@ static inline int big_propagators(BigState* s, const double* x_dev, double2* out
   return QOC_OK;
 }
 
-static inline int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStream_t st, std::string& err, qoc_stats& stats) {
+int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStream_t st, std::string& err, qoc_stats& stats) {
   const qoc_desc& d = s->d;
   const size_t DD = s->DD;
   int rc;

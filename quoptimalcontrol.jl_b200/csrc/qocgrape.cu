@@ -1,9 +1,8 @@
 // libqocgrape.so — host orchestration + C ABI (include/qocgrape.h).  No CPU fallback anywhere: every
 // entry point either runs the sm_100a kernels or returns an error.
 #include "../../include/qocgrape.h"
-#include "small_d.cuh"
-#include "small_phased.cuh"
-#include "big_d.cuh"
+#include "params.h"
+#include "big_api.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -55,8 +54,19 @@ struct qoc_handle {
   char* comm_peer_host[QOC_MAX_RANKS] = {};
   char** comm_peers = nullptr;           // device array of the peers' base pointers
   int comm_world = 0, comm_rank = -1;
-  unsigned long long comm_epoch = 0;
+  unsigned long long* comm_ctl = nullptr;   // device: [0] epoch of the last finished all-reduce, [1] / [2] block tickets
   size_t comm_n = 0;
+  cudaGraphExec_t ar_graph[2] = {nullptr, nullptr};      // qoc_eval_allreduce (host buffers): [0] value only, [1] + gradient
+  int ar_launches[2] = {0, 0};
+  cudaGraphExec_t ard_graph[2] = {nullptr, nullptr};     // qoc_eval_allreduce_device, cached for one (x_dev, FG_dev) pair
+  const double* ard_x[2] = {nullptr, nullptr};
+  double* ard_fg[2] = {nullptr, nullptr};
+  int ard_launches[2] = {0, 0};
+  // control penalties C3 / C4 (qoc_set_penalty)
+  double pen_amp = 0.0, pen_var = 0.0;
+  // single-process multi-device parent (qoc_desc.n_devices > 1): the members are sharded over sub-handles
+  struct MultiState* multi = nullptr;
+  bool is_sub = false;
 };
 
 #define QOC_CUDA(h, call)                                                                           \
@@ -79,32 +89,14 @@ extern "C" const char* qoc_version(void) { return "qocgrape-b200 0.1 (sm_100a, D
 
 extern "C" const char* qoc_last_error(qoc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-// ------------------------------------------------------------------------------------------------ dispatch
-typedef void (*chain_fn)(const SmallParams);
-template <int NB, int CPW> static chain_fn pick_chain2(int sys, int grad) {
-  if (sys == SYS_UNITARY) {
-    if (grad == GRAD_NONE) return chain_kernel<NB, CPW, SYS_UNITARY, GRAD_NONE>;
-    if (grad == GRAD_FIRST) return chain_kernel<NB, CPW, SYS_UNITARY, GRAD_FIRST>;
-    return chain_kernel<NB, CPW, SYS_UNITARY, GRAD_EXACT>;
-  }
-  if (grad == GRAD_NONE) return chain_kernel<NB, CPW, SYS_DENSITY, GRAD_NONE>;
-  if (grad == GRAD_FIRST) return chain_kernel<NB, CPW, SYS_DENSITY, GRAD_FIRST>;
-  return chain_kernel<NB, CPW, SYS_DENSITY, GRAD_EXACT>;
-}
-static chain_fn pick_chain(int NB, int CPW, int sys, int grad) {
-  if (NB == 2) return pick_chain2<2, 1>(sys, grad);
-  if (CPW == 4) return pick_chain2<1, 4>(sys, grad);
-  if (CPW == 2) return pick_chain2<1, 2>(sys, grad);
-  return pick_chain2<1, 1>(sys, grad);
-}
-typedef void (*slice_fn)(const SliceParams);
-static slice_fn pick_slices(int NB, int CPW) {
-  if (NB == 2) return expm_slices_kernel<2, 1>;
-  if (CPW == 4) return expm_slices_kernel<1, 4>;
-  if (CPW == 2) return expm_slices_kernel<1, 2>;
-  return expm_slices_kernel<1, 1>;
-}
+static int multi_create(qoc_handle** out, const qoc_desc& d, int ndev);
+static void multi_destroy(qoc_handle* h);
+static int multi_set_system(qoc_handle* h, const double* A, const double* B, const double* Xi, const double* Xt, const double* wts, int shared_flags);
+static int multi_eval(qoc_handle* h, const double* x, double* F, double* G);
+static void multi_drop_graphs(qoc_handle* h);
+static void multi_stats(qoc_handle* h);
 
+// ------------------------------------------------------------------------------------------------ launch bookkeeping
 static int launch_check(qoc_handle* h, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { h->err = std::string(what) + ": " + cudaGetErrorString(e); return QOC_ECUDA; }
@@ -127,6 +119,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     g_create_error = std::string("qoc_create: no CUDA device (") + cudaGetErrorString(ce) + "); there is no CPU fallback";
     return QOC_ECUDA;
   }
+  if (d.n_devices > 1) return multi_create(out, d, ndev);
   if (d.device < 0 || d.device >= ndev) { g_create_error = "qoc_create: bad device ordinal"; return QOC_EINVAL; }
   qoc_handle* h = new qoc_handle();
   h->d = d;
@@ -236,15 +229,24 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
   return QOC_OK;
 }
 
+static void drop_graphs(qoc_handle* h) {
+  for (cudaGraphExec_t* arr : {h->graph_exec, h->ar_graph, h->ard_graph})
+    for (int i = 0; i < 2; i++) { if (arr[i]) cudaGraphExecDestroy(arr[i]); arr[i] = nullptr; }
+  h->graph_launches[0] = h->graph_launches[1] = 0;
+  h->ard_x[0] = h->ard_x[1] = nullptr;
+}
+
 extern "C" int qoc_destroy(qoc_handle* h) {
   if (!h) return QOC_OK;
+  if (h->multi) { multi_destroy(h); delete h; return QOC_OK; }
   cudaSetDevice(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->big) big_destroy(h->big);
-  for (auto& g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
+  drop_graphs(h);
   for (int r = 0; r < h->comm_world; r++) if (r != h->comm_rank && h->comm_peer_host[r]) cudaIpcCloseMemHandle(h->comm_peer_host[r]);
   if (h->comm_local) cudaFree(h->comm_local);
   if (h->comm_peers) cudaFree(h->comm_peers);
+  if (h->comm_ctl) cudaFree(h->comm_ctl);
   void* bufs[] = {h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
@@ -265,7 +267,7 @@ static int pack_one(qoc_handle* h, const double2* src_dev, int n_src, long src_s
   pp.D = h->d.D; pp.NB = h->NB; pp.CPW = h->CPW; pp.n_og = h->n_sysgroups; pp.nmat_dst = nmat_dst; pp.mat_dst = mat_dst;
   pp.transpose = transpose; pp.pack_mode = pack_mode; pp.n_src = n_src; pp.src_stride = src_stride; pp.src = src_dev; pp.dst = dst;
   long total = (long)h->n_sysgroups * h->NB * h->NB * 64;
-  pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(pp);
+  launch_pack(pp, total, h->stream);
   return launch_check(h, "pack_kernel");
 }
 
@@ -273,7 +275,11 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
                               const double* wts, int shared_flags) {
   if (!h) return QOC_EINVAL;
   if (!A || !Xi || !Xt || (h->d.K > 0 && !B)) { h->err = "qoc_set_system: null matrix argument"; return QOC_EINVAL; }
+  if (h->multi) return multi_set_system(h, A, B, Xi, Xt, wts, shared_flags);
   QOC_CUDA(h, cudaSetDevice(h->d.device));
+  // a captured evaluation bakes in the Hermitian / closed-system kernel choice of the system it was captured for
+  QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  drop_graphs(h);
   const qoc_desc& d = h->d;
   const size_t DD = (size_t)d.D * d.D;
   std::vector<double> w(d.M, 1.0);
@@ -282,7 +288,7 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
   QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->path == 2) {
     int rc = big_set_system(h->big, A, B, Xi, Xt, shared_flags, h->err);
-    if (rc == QOC_OK) { h->system_set = true; h->st.path = h->big->pure.active ? 3 : 2; }
+    if (rc == QOC_OK) { h->system_set = true; h->st.path = big_pure_active(h->big) ? 3 : 2; }
     return rc;
   }
   // small path: stage raw matrices on the device, then pack into the warp layout
@@ -379,12 +385,7 @@ static int launch_chain(qoc_handle* h, const SmallParams& p, int sys, int grad, 
 }
 // closed-system kernel (Hermitian drift and controls, first-order gradient, fused mode)
 static int launch_chain_unitary(qoc_handle* h, const SmallParams& p, int sys, cudaStream_t st) {
-  chain_fn fn;
-  const bool u = sys == SYS_UNITARY;
-  if (h->NB == 2) fn = u ? chain_unitary_kernel<2, 1, SYS_UNITARY> : chain_unitary_kernel<2, 1, SYS_DENSITY>;
-  else if (h->CPW == 4) fn = u ? chain_unitary_kernel<1, 4, SYS_UNITARY> : chain_unitary_kernel<1, 4, SYS_DENSITY>;
-  else if (h->CPW == 2) fn = u ? chain_unitary_kernel<1, 2, SYS_UNITARY> : chain_unitary_kernel<1, 2, SYS_DENSITY>;
-  else fn = u ? chain_unitary_kernel<1, 1, SYS_UNITARY> : chain_unitary_kernel<1, 1, SYS_DENSITY>;
+  chain_fn fn = pick_chain_unitary(h->NB, h->CPW, sys);
   if (h->smem_bytes > 48 * 1024)
     QOC_CUDA(h, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
   fn<<<(unsigned)((h->n_groups + 3) / 4), 128, h->smem_bytes, st>>>(p);
@@ -408,19 +409,6 @@ static PhasedParams phased_params(qoc_handle* h, const double* x_dev) {
   return p;
 }
 
-// dispatch of the phased-pipeline kernels
-typedef void (*phased_fn)(const PhasedParams);
-template <int NB, int CPW> static void pick_phased(int sys, int grad, phased_fn& tot, phased_fn& bnd, phased_fn& swp, phased_fn& grd) {
-  tot = chunk_totals_kernel<NB, CPW>;
-  if (sys == SYS_UNITARY) {
-    bnd = boundary_kernel<NB, CPW, SYS_UNITARY>; swp = sweep_kernel<NB, CPW, SYS_UNITARY>;
-    grd = grad == GRAD_EXACT ? grad_slices_kernel<NB, CPW, SYS_UNITARY, GRAD_EXACT> : grad_slices_kernel<NB, CPW, SYS_UNITARY, GRAD_FIRST>;
-  } else {
-    bnd = boundary_kernel<NB, CPW, SYS_DENSITY>; swp = sweep_kernel<NB, CPW, SYS_DENSITY>;
-    grd = grad == GRAD_EXACT ? grad_slices_kernel<NB, CPW, SYS_DENSITY, GRAD_EXACT> : grad_slices_kernel<NB, CPW, SYS_DENSITY, GRAD_FIRST>;
-  }
-}
-
 static int eval_phased(qoc_handle* h, const double* x_dev, int sys, int grad, cudaStream_t st) {
   const qoc_desc& d = h->d;
   int rc;
@@ -429,10 +417,7 @@ static int eval_phased(qoc_handle* h, const double* x_dev, int sys, int grad, cu
   if ((rc = launch_slices(h, s, st)) != QOC_OK) return rc;
   PhasedParams p = phased_params(h, x_dev);
   phased_fn tot, bnd, swp, grd;
-  if (h->NB == 2) pick_phased<2, 1>(sys, grad, tot, bnd, swp, grd);
-  else if (h->CPW == 4) pick_phased<1, 4>(sys, grad, tot, bnd, swp, grd);
-  else if (h->CPW == 2) pick_phased<1, 2>(sys, grad, tot, bnd, swp, grd);
-  else pick_phased<1, 1>(sys, grad, tot, bnd, swp, grd);
+  pick_phased(h->NB, h->CPW, sys, grad, tot, bnd, swp, grd);
   auto blocks = [](long warps) { return (unsigned)((warps + 3) / 4); };
   if (h->Cn > 1) {
     tot<<<blocks((long)h->n_groups * h->Cn), 128, h->tb_bytes, st>>>(p);
@@ -454,24 +439,15 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
   const size_t sys_bytes = (size_t)4 * (1 + h->d.K) * E * sizeof(double2);
   p.sys_in_smem = sys_bytes + h->tb_bytes <= 96 * 1024;
   const int smem1 = h->tb_bytes + (p.sys_in_smem ? (int)sys_bytes : 0);
-  typedef void (*kfn)(const PhasedParams);
-  kfn k1, k2;
-  if (h->NB == 2) { k1 = chunk_expm_kernel<2, 1>; k2 = sys == SYS_UNITARY ? boundary2_kernel<2, 1, SYS_UNITARY> : boundary2_kernel<2, 1, SYS_DENSITY>; }
-  else if (h->CPW == 4) { k1 = chunk_expm_kernel<1, 4>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 4, SYS_UNITARY> : boundary2_kernel<1, 4, SYS_DENSITY>; }
-  else if (h->CPW == 2) { k1 = chunk_expm_kernel<1, 2>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 2, SYS_UNITARY> : boundary2_kernel<1, 2, SYS_DENSITY>; }
-  else { k1 = chunk_expm_kernel<1, 1>; k2 = sys == SYS_UNITARY ? boundary2_kernel<1, 1, SYS_UNITARY> : boundary2_kernel<1, 1, SYS_DENSITY>; }
+  typedef phased_fn kfn;
+  kfn k1 = pick_chunk_expm(h->NB, h->CPW), k2 = pick_boundary2(h->NB, h->CPW, sys);
   if (smem1 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
   const bool closed = grad == GRAD_FIRST && h->herm && h->unitary_fast;     // closed-system conjugation recursion
   p.store_plain = closed;
   k1<<<(unsigned)(((long)h->n_groups * h->Cn + 3) / 4), 128, smem1, st>>>(p);
   if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
   if (closed) {
-    kfn kb, ks;
-    const bool u = sys == SYS_UNITARY;
-    if (h->NB == 2) { kb = u ? boundary_unitary_kernel<2, 1, SYS_UNITARY> : boundary_unitary_kernel<2, 1, SYS_DENSITY>; ks = sweep_unitary_kernel<2, 1>; }
-    else if (h->CPW == 4) { kb = u ? boundary_unitary_kernel<1, 4, SYS_UNITARY> : boundary_unitary_kernel<1, 4, SYS_DENSITY>; ks = sweep_unitary_kernel<1, 4>; }
-    else if (h->CPW == 2) { kb = u ? boundary_unitary_kernel<1, 2, SYS_UNITARY> : boundary_unitary_kernel<1, 2, SYS_DENSITY>; ks = sweep_unitary_kernel<1, 2>; }
-    else { kb = u ? boundary_unitary_kernel<1, 1, SYS_UNITARY> : boundary_unitary_kernel<1, 1, SYS_DENSITY>; ks = sweep_unitary_kernel<1, 1>; }
+    kfn kb = pick_boundary_unitary(h->NB, h->CPW, sys), ks = pick_sweep_unitary(h->NB, h->CPW);
     kb<<<(unsigned)((h->n_groups + 3) / 4), 128, h->tb_bytes, st>>>(p);
     if ((rc = launch_check(h, "boundary_unitary_kernel")) != QOC_OK) return rc;
     const size_t bbytes = (size_t)4 * h->d.K * E * sizeof(double2);
@@ -487,7 +463,9 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
   return launch_chain(h, cp, sys, grad, st);
 }
 
-static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int want_grad, cudaStream_t st) {
+// rows_only: stop after the first reduction pass and leave the partial rows [R][red_nchunks][NK+1] in h->part (the
+// all-reduce kernel folds them); otherwise fg_dev receives the finished [R][NK+1] rows.
+static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int want_grad, cudaStream_t st, bool rows_only = false) {
   const qoc_desc& d = h->d;
   int rc;
   SmallParams p = small_params(h, x_dev);
@@ -510,25 +488,76 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
     if ((rc = launch_chain(h, p, sys, grad, st)) != QOC_OK) return rc;
   }
   if (!h->in_capture) { QOC_CUDA(h, cudaEventRecord(h->ek1[slot], st)); h->kring_count++; }
-  dim3 g1((unsigned)(((h->NK + 1 + 255) / 256) * (long)d.R), h->red_nchunks);
-  reduce_members_pass1<<<g1, 256, 0, st>>>(want_grad ? h->gradc : nullptr, h->fomc, h->wts, h->red_nchunks == 1 ? fg_dev : h->part, d.M, h->NK,
-                                           h->red_chunk, h->red_nchunks);
+  const bool direct = h->red_nchunks == 1 && !rows_only;
+  launch_reduce_pass1(want_grad ? h->gradc : nullptr, h->fomc, h->wts, direct ? fg_dev : h->part, d.M, h->NK, d.R,
+                      h->red_chunk, h->red_nchunks, st);
   if ((rc = launch_check(h, "reduce_members_pass1")) != QOC_OK) return rc;
-  if (h->red_nchunks == 1) return QOC_OK;
-  dim3 g2((unsigned)(((h->NK + 1 + 31) / 32) * (long)d.R));
-  reduce_members_pass2<<<g2, 32 * RED_LANES, 0, st>>>(h->part, fg_dev, h->NK, h->red_nchunks);
+  if (direct || rows_only) return QOC_OK;
+  launch_reduce_pass2(h->part, fg_dev, h->NK, d.R, h->red_nchunks, st);
   return launch_check(h, "reduce_members_pass2");
 }
 
-static int eval_device_on(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, cudaStream_t st) {
+// ------------------------------------------------------------------------------------------------ control penalties
+// F += w_amp * C3(x) + w_var * C4(x)  (src/cost_functions.jl:29-39) and the matching gradient, one block per pulse, fixed
+// summation order.  x [R][N][K], FG [R][1 + N*K].
+__global__ void __launch_bounds__(256) penalty_kernel(const double* __restrict__ x, double* __restrict__ FG, int N, int K, double wa, double wv,
+                                                      int want_grad) {
+  __shared__ double sm[256];
+  const int NK = N * K;
+  const double* xr = x + (size_t)blockIdx.x * NK;
+  double* fg = FG + (size_t)blockIdx.x * (NK + 1);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < NK; i += blockDim.x) {
+    const double xi = xr[i];
+    acc = fma(wa * xi, xi, acc);
+    double g = 2.0 * wa * xi;
+    if (i + K < NK) { const double dn = xr[i + K] - xi; acc = fma(wv * dn, dn, acc); g -= 2.0 * wv * dn; }   // slice t+1 minus slice t
+    if (i >= K) g += 2.0 * wv * (xi - xr[i - K]);
+    if (want_grad) fg[1 + i] += g;
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) fg[0] += sm[0];
+}
+static int apply_penalty(qoc_handle* h, const double* x_dev, double* FG_dev, int want_grad, cudaStream_t st) {
+  if (h->pen_amp == 0.0 && h->pen_var == 0.0) return QOC_OK;
+  penalty_kernel<<<h->d.R, 256, 0, st>>>(x_dev, FG_dev, h->d.N, h->d.K, h->pen_amp, h->pen_var, want_grad);
+  return launch_check(h, "penalty_kernel");
+}
+
+extern "C" int qoc_set_penalty(qoc_handle* h, double w_amp, double w_var) {
+  if (!h) return QOC_EINVAL;
+  if (!(w_amp == w_amp) || !(w_var == w_var)) { h->err = "qoc_set_penalty: NaN weight"; return QOC_EINVAL; }
+  if (w_amp != h->pen_amp || w_var != h->pen_var) {       // captured graphs bake the weights in
+    if (h->stream) { cudaSetDevice(h->d.device); cudaStreamSynchronize(h->stream); }
+    drop_graphs(h);
+    multi_drop_graphs(h);
+  }
+  h->pen_amp = w_amp; h->pen_var = w_var;
+  return QOC_OK;
+}
+
+// the ensemble-reduced rows without penalties (what a shard contributes to a cross-device sum)
+static int eval_core(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, cudaStream_t st) {
   h->st.launches_last_eval = 0;
   h->st.n_evals++;
-  if (h->path == 2) return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st, h->big_reuse);
+  if (h->path == 2) {
+    if (!want_gradient)     // the D > 16 kernels only write the F column of a value-only evaluation
+      QOC_CUDA(h, cudaMemsetAsync(FG_dev, 0, (size_t)h->d.R * (h->NK + 1) * sizeof(double), st));
+    return big_eval(h->big, x_dev, FG_dev, want_gradient, h->wts, st, h->err, h->st, h->big_reuse);
+  }
   return eval_small(h, x_dev, FG_dev, want_gradient, st);
+}
+static int eval_device_on(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, cudaStream_t st) {
+  int rc = eval_core(h, x_dev, FG_dev, want_gradient, st);
+  if (rc != QOC_OK) return rc;
+  return apply_penalty(h, x_dev, FG_dev, want_gradient, st);
 }
 
 extern "C" int qoc_eval_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream) {
   if (!h) return QOC_EINVAL;
+  if (h->multi) { h->err = "qoc_eval_device: not available on a multi-device handle (use qoc_eval)"; return QOC_EUNSUPPORTED; }
   if (!x_dev || !FG_dev) { h->err = "qoc_eval_device: null pointer"; return QOC_EINVAL; }
   if (!h->system_set) { h->err = "qoc_eval_device: qoc_set_system has not been called"; return QOC_EINVAL; }
   QOC_CUDA(h, cudaSetDevice(h->d.device));
@@ -542,43 +571,65 @@ static cudaError_t copy_result_async(qoc_handle* h, bool grad) {
   return cudaMemcpy2DAsync(h->hout, row * sizeof(double), h->out, row * sizeof(double), sizeof(double), h->d.R, cudaMemcpyDeviceToHost, h->stream);
 }
 
+// Captures `body` (everything it enqueues on h->stream) into a CUDA graph; on failure *exec stays null.
+template <class Body> static bool capture_graph(qoc_handle* h, cudaGraphExec_t* exec, int* n_launches, Body body) {
+  if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+  h->in_capture = true;
+  const long long before = h->st.n_launches;
+  const bool ok = body();
+  h->in_capture = false;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  *n_launches = (int)(h->st.n_launches - before);
+  h->st.n_launches = before;
+  if (!ok || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return false; }
+  e = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { *exec = nullptr; cudaGetLastError(); return false; }
+  return true;
+}
+
 // Captures H2D(x) -> kernels -> D2H([F|G]) once per variant and replays it afterwards: one graph launch per
 // evaluation.  Everything in the sequence is static (pinned staging buffers, device buffers, launch geometry).
+// The replay is bracketed by the kernel-ring events, so qoc_stats.main_kernel_ms_avg is the graph's device time.
 static bool eval_via_graph(qoc_handle* h, bool grad) {
   const int gi = grad ? 1 : 0;
   const size_t nx = (size_t)h->d.R * h->NK;
   if (!h->graph_exec[gi]) {
-    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
-    h->in_capture = true;
-    const long long before = h->st.n_launches;
-    bool ok = cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
-    ok = ok && eval_small(h, h->x, h->out, grad, h->stream) == QOC_OK;
-    ok = ok && copy_result_async(h, grad) == cudaSuccess;
-    h->in_capture = false;
-    cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-    h->graph_launches[gi] = (int)(h->st.n_launches - before);
-    h->st.n_launches = before;
-    if (!ok || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return false; }
-    e = cudaGraphInstantiate(&h->graph_exec[gi], graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { h->graph_exec[gi] = nullptr; cudaGetLastError(); return false; }
+    const bool ok = capture_graph(h, &h->graph_exec[gi], &h->graph_launches[gi], [&]() {
+      bool k = cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+      k = k && eval_device_on(h, h->x, h->out, grad, h->stream) == QOC_OK;
+      return k && copy_result_async(h, grad) == cudaSuccess;
+    });
+    h->st.n_evals--;                      // the capture pass evaluated nothing
+    if (!ok) return false;
   }
+  const int slot = h->kring_count % qoc_handle::KRING;
+  cudaEventRecord(h->ek0[slot], h->stream);
   if (cudaGraphLaunch(h->graph_exec[gi], h->stream) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaEventRecord(h->ek1[slot], h->stream); h->kring_count++;
   h->st.n_launches += h->graph_launches[gi];
   h->st.launches_last_eval = h->graph_launches[gi];
   return cudaStreamSynchronize(h->stream) == cudaSuccess;
+}
+
+static void unpack_result(qoc_handle* h, const double* hout, double* F, double* G) {
+  const size_t row = (size_t)h->NK + 1;
+  for (int r = 0; r < h->d.R; r++) {
+    if (F) F[r] = hout[r * row];
+    if (G) memcpy(G + (size_t)r * h->NK, hout + r * row + 1, sizeof(double) * h->NK);
+  }
 }
 
 extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
   if (!h) return QOC_EINVAL;
   if (!x) { h->err = "qoc_eval: null pulse"; return QOC_EINVAL; }
   if (!h->system_set) { h->err = "qoc_eval: qoc_set_system has not been called"; return QOC_EINVAL; }
+  if (h->multi) return multi_eval(h, x, F, G);
   const qoc_desc& d = h->d;
   QOC_CUDA(h, cudaSetDevice(d.device));
   const size_t nx = (size_t)d.R * h->NK;
   memcpy(h->hx, x, nx * sizeof(double));
-  const size_t row = (size_t)h->NK + 1;
   bool done = false;
   if (h->path == 1 && h->use_graph) {
     h->st.n_evals++;
@@ -596,16 +647,14 @@ extern "C" int qoc_eval(qoc_handle* h, const double* x, double* F, double* G) {
     QOC_CUDA(h, cudaStreamSynchronize(h->stream));
     QOC_CUDA(h, cudaEventElapsedTime(&h->st.gpu_ms_last_eval, h->ev0, h->ev1));
   }
-  for (int r = 0; r < d.R; r++) {
-    if (F) F[r] = h->hout[r * row];
-    if (G) memcpy(G + (size_t)r * h->NK, h->hout + r * row + 1, sizeof(double) * h->NK);
-  }
+  unpack_result(h, h->hout, F, G);
   return QOC_OK;
 }
 
 // Slice-parallel use (one rank per range of slices): new boundary operators per evaluation, drift and controls stay.
 extern "C" int qoc_set_states(qoc_handle* h, const double* Xi, const double* Xt, int shared_flags) {
   if (!h) return QOC_EINVAL;
+  if (h->multi) { h->err = "qoc_set_states: not available on a multi-device handle"; return QOC_EUNSUPPORTED; }
   if (!Xi || !Xt) { h->err = "qoc_set_states: null pointer"; return QOC_EINVAL; }
   if (!h->system_set) { h->err = "qoc_set_states: qoc_set_system has not been called"; return QOC_EINVAL; }
   if (h->path != 2) { h->err = "qoc_set_states: only implemented for D > 16 (tiled GEMM path)"; return QOC_EUNSUPPORTED; }
@@ -617,6 +666,7 @@ extern "C" int qoc_set_states(qoc_handle* h, const double* Xi, const double* Xt,
 // F (and G) for the pulse of the immediately preceding qoc_total_propagator call, reusing its propagators and chunk totals.
 extern "C" int qoc_eval_continue(qoc_handle* h, double* F, double* G) {
   if (!h) return QOC_EINVAL;
+  if (h->multi) { h->err = "qoc_eval_continue: not available on a multi-device handle"; return QOC_EUNSUPPORTED; }
   if (!h->system_set) { h->err = "qoc_eval_continue: qoc_set_system has not been called"; return QOC_EINVAL; }
   if (h->path != 2) { h->err = "qoc_eval_continue: only implemented for D > 16 (tiled GEMM path)"; return QOC_EUNSUPPORTED; }
   const qoc_desc& d = h->d;
@@ -654,6 +704,7 @@ static int upload_x(qoc_handle* h, const double* x) {
 
 extern "C" int qoc_total_propagator(qoc_handle* h, const double* x, double* U) {
   if (!h) return QOC_EINVAL;
+  if (h->multi) { h->err = "qoc_total_propagator: not available on a multi-device handle"; return QOC_EUNSUPPORTED; }
   if (!x || !U) { h->err = "qoc_total_propagator: null pointer"; return QOC_EINVAL; }
   if (!h->system_set) { h->err = "qoc_total_propagator: qoc_set_system has not been called"; return QOC_EINVAL; }
   const qoc_desc& d = h->d;
@@ -677,6 +728,7 @@ extern "C" int qoc_total_propagator(qoc_handle* h, const double* x, double* U) {
 
 extern "C" int qoc_propagators(qoc_handle* h, const double* x, double* out, int mode) {
   if (!h) return QOC_EINVAL;
+  if (h->multi) { h->err = "qoc_propagators: not available on a multi-device handle"; return QOC_EUNSUPPORTED; }
   if (!x || !out || mode < 0 || mode > 2) { h->err = "qoc_propagators: bad argument"; return QOC_EINVAL; }
   if (!h->system_set) { h->err = "qoc_propagators: qoc_set_system has not been called"; return QOC_EINVAL; }
   const qoc_desc& d = h->d;
@@ -699,42 +751,101 @@ extern "C" int qoc_propagators(qoc_handle* h, const double* x, double* out, int 
 }
 
 // ------------------------------------------------------------------------------------------------ one-shot all-reduce
-// Exchange buffer layout per rank: double data[2][n]; unsigned long long flags[2][QOC_MAX_RANKS].
-// Epoch e uses half b = e & 1.  A rank can only be one epoch ahead of its slowest peer (it needs that peer's flag to
-// finish an epoch), so two halves suffice: nobody overwrites a half that a peer may still be reading.
-__global__ void oneshot_allreduce_kernel(char* const* peers, int world, int rank, unsigned long long epoch, size_t n,
-                                         double* __restrict__ out) {
+// Exchange buffer layout per rank: double data[2][n]; unsigned long long flags[2][QOC_MAX_RANKS]  (n = R * (NK + 1)).
+// The kernel (i) folds this rank's partial rows of the member reduction (the former second reduction pass) into its half
+// b = epoch & 1 of the exchange buffer, (ii) the last block to finish that raises this rank's flag in every peer,
+// (iii) every block waits for all ranks' flags in its OWN flag array (local polls; the own flag doubles as the grid
+// barrier), (iv) sums the ranks' rows in fixed rank order (bit-identical on every rank).
+// The epoch lives in device memory (ctl[0] = last finished epoch; ctl[1], ctl[2] = block tickets), so the launch has no
+// per-call arguments and the whole evaluation can be replayed from a CUDA graph.
+// Two halves suffice: a rank can only be one epoch ahead of its slowest peer (finishing an epoch needs that peer's flag,
+// which the peer raises after it has left the previous epoch's kernel), so nobody overwrites a half that is still read.
+// The grid never exceeds the SM count (all blocks co-resident: the flag wait is a spin).
+constexpr int AR_ELEMS = 32, AR_LANES = 8;      // block = 32 elements x 8 lanes (partial rows / ranks interleaved)
+__global__ void __launch_bounds__(AR_ELEMS * AR_LANES)
+reduce_allreduce_kernel(const double* __restrict__ part, int nrows, int NK, int R, char* const* peers, int world, int rank,
+                        unsigned long long* ctl, double* __restrict__ out) {
+  __shared__ double sm[AR_LANES][AR_ELEMS + 1];
+  __shared__ int is_last;
+  const size_t n = (size_t)R * (NK + 1);
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long*>(ctl) + 1;
   const int b = (int)(epoch & 1);
   const size_t flags_off = 2 * n * sizeof(double);
-  if (blockIdx.x == 0 && threadIdx.x < world) {
-    // this rank's partial was written by the preceding kernel on the same stream; publish it system-wide, then signal
-    __threadfence_system();
-    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + flags_off) + b * QOC_MAX_RANKS + rank;
-    *f = epoch;
+  const int el = threadIdx.x & (AR_ELEMS - 1), lane = threadIdx.x / AR_ELEMS;
+  const size_t ngroups = (n + AR_ELEMS - 1) / AR_ELEMS;
+  double* mine = reinterpret_cast<double*>(peers[rank]) + (size_t)b * n;
+  // (i) local fold of the partial rows [R][nrows][NK+1]
+  for (size_t gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
+    const size_t i = gidx * AR_ELEMS + el;
+    double s = 0.0;
+    if (i < n) {
+      const size_t r = i / (NK + 1), e = i - r * (NK + 1);
+      for (int ch = lane; ch < nrows; ch += AR_LANES) s += part[(r * nrows + ch) * (NK + 1) + e];
+    }
+    sm[lane][el] = s;
+    __syncthreads();
+    if (lane == 0 && i < n) {
+      double t = sm[0][el];
+#pragma unroll
+      for (int l = 1; l < AR_LANES; l++) t += sm[l][el];
+      mine[i] = t;
+    }
+    __syncthreads();
   }
-  // wait for every peer's signal in OUR flag array (local memory polls)
-  const volatile unsigned long long* mine = reinterpret_cast<const volatile unsigned long long*>(peers[rank] + flags_off) + b * QOC_MAX_RANKS;
-  if (threadIdx.x < world) { while (mine[threadIdx.x] < epoch) __nanosleep(64); }
+  // (ii) publish: the last block to get here knows every block's rows are written
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned long long old = atomicAdd(&ctl[1], 1ULL);
+    is_last = old == (unsigned long long)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x == 0) ctl[1] = 0;
+    __threadfence_system();
+    if (threadIdx.x < world) {
+      volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + flags_off) + b * QOC_MAX_RANKS + rank;
+      *f = epoch;
+    }
+  }
+  // (iii) wait for every rank's flag (own flag included) in OUR flag array
+  const volatile unsigned long long* flg = reinterpret_cast<const volatile unsigned long long*>(peers[rank] + flags_off) + b * QOC_MAX_RANKS;
+  if (threadIdx.x < world) { while (flg[threadIdx.x] < epoch) __nanosleep(32); }
   __syncthreads();
   __threadfence_system();
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  // (iv) sum over ranks in fixed order
+  for (size_t gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
+    const size_t i = gidx * AR_ELEMS + el;
     double s = 0.0;
-    for (int r = 0; r < world; r++) {
-      const volatile double* src = reinterpret_cast<const volatile double*>(peers[r]) + (size_t)b * n;
-      s += src[i];                                   // fixed rank order: bit-identical on every rank
+    if (i < n)
+      for (int r = lane; r < world; r += AR_LANES) s += (reinterpret_cast<const volatile double*>(peers[r]) + (size_t)b * n)[i];
+    sm[lane][el] = s;
+    __syncthreads();
+    if (lane == 0 && i < n) {
+      double t = sm[0][el];
+#pragma unroll
+      for (int l = 1; l < AR_LANES; l++) t += sm[l][el];
+      out[i] = t;
     }
-    out[i] = s;
+    __syncthreads();
+  }
+  // the last block to leave advances the epoch for the next launch
+  if (threadIdx.x == 0) {
+    const unsigned long long old = atomicAdd(&ctl[2], 1ULL);
+    if (old == (unsigned long long)gridDim.x - 1) { ctl[2] = 0; ctl[0] = epoch; __threadfence(); }
   }
 }
 
 extern "C" int qoc_comm_export(qoc_handle* h, unsigned char* handle) {
   if (!h || !handle) return QOC_EINVAL;
+  if (h->multi) { h->err = "qoc_comm_export: a multi-device handle already sums its devices"; return QOC_EUNSUPPORTED; }
   QOC_CUDA(h, cudaSetDevice(h->d.device));
   if (!h->comm_local) {
     h->comm_n = (size_t)h->d.R * (h->NK + 1);
     const size_t bytes = 2 * h->comm_n * sizeof(double) + 2 * QOC_MAX_RANKS * sizeof(unsigned long long);
     QOC_CUDA(h, cudaMalloc((void**)&h->comm_local, bytes));
     QOC_CUDA(h, cudaMemset(h->comm_local, 0, bytes));
+    QOC_CUDA(h, cudaMalloc((void**)&h->comm_ctl, 4 * sizeof(unsigned long long)));
+    QOC_CUDA(h, cudaMemset(h->comm_ctl, 0, 4 * sizeof(unsigned long long)));
     QOC_CUDA(h, cudaDeviceSynchronize());
     h->ws_bytes += (long long)bytes;
   }
@@ -748,6 +859,8 @@ extern "C" int qoc_comm_export(qoc_handle* h, unsigned char* handle) {
 extern "C" int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsigned char* handles) {
   if (!h || !handles || world < 1 || world > QOC_MAX_RANKS || rank < 0 || rank >= world) { if (h) h->err = "qoc_comm_connect: bad argument"; return QOC_EINVAL; }
   if (!h->comm_local) { h->err = "qoc_comm_connect: call qoc_comm_export first"; return QOC_EINVAL; }
+  // the epoch protocol assumes every rank's counters start together: a second connect would meet stale flags
+  if (h->comm_world > 0) { h->err = "qoc_comm_connect: this handle is already connected (once per handle)"; return QOC_EINVAL; }
   QOC_CUDA(h, cudaSetDevice(h->d.device));
   for (int r = 0; r < world; r++) {
     if (r == rank) { h->comm_peer_host[r] = h->comm_local; continue; }
@@ -759,25 +872,330 @@ extern "C" int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsign
   }
   if (!h->comm_peers) QOC_CUDA(h, cudaMalloc((void**)&h->comm_peers, QOC_MAX_RANKS * sizeof(char*)));
   QOC_CUDA(h, cudaMemcpy(h->comm_peers, h->comm_peer_host, QOC_MAX_RANKS * sizeof(char*), cudaMemcpyHostToDevice));
-  h->comm_world = world; h->comm_rank = rank; h->comm_epoch = 0;
+  h->comm_world = world; h->comm_rank = rank;
+  return QOC_OK;
+}
+
+// kernels of one sharded evaluation on `st`: chains -> first reduction pass -> fused fold + all-reduce -> penalties
+static int enqueue_allreduce(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, cudaStream_t st) {
+  int rc;
+  const double* rows; int nrows;
+  h->st.launches_last_eval = 0;
+  h->st.n_evals++;
+  if (h->path == 2) {                       // D > 16: the GEMM pipeline delivers finished rows
+    if (!want_gradient) QOC_CUDA(h, cudaMemsetAsync(h->part, 0, (size_t)h->d.R * (h->NK + 1) * sizeof(double), st));
+    if ((rc = big_eval(h->big, x_dev, h->part, want_gradient, h->wts, st, h->err, h->st, false)) != QOC_OK) return rc;
+    rows = h->part; nrows = 1;
+  } else {
+    if ((rc = eval_small(h, x_dev, nullptr, want_gradient, st, true)) != QOC_OK) return rc;
+    rows = h->part; nrows = h->red_nchunks;
+  }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->d.device);
+  const int blocks = (int)std::min<size_t>((h->comm_n + AR_ELEMS - 1) / AR_ELEMS, (size_t)nsm);
+  reduce_allreduce_kernel<<<blocks, AR_ELEMS * AR_LANES, 0, st>>>(rows, nrows, h->NK, h->d.R, h->comm_peers, h->comm_world, h->comm_rank,
+                                                                 h->comm_ctl, FG_dev);
+  if ((rc = launch_check(h, "reduce_allreduce_kernel")) != QOC_OK) return rc;
+  return apply_penalty(h, x_dev, FG_dev, want_gradient, st);
+}
+
+static int allreduce_ready(qoc_handle* h, const char* who) {
+  if (h->multi) { h->err = std::string(who) + ": not available on a multi-device handle"; return QOC_EUNSUPPORTED; }
+  if (!h->system_set) { h->err = std::string(who) + ": qoc_set_system has not been called"; return QOC_EINVAL; }
+  if (h->comm_world < 1) { h->err = std::string(who) + ": qoc_comm_connect has not been called"; return QOC_EINVAL; }
   return QOC_OK;
 }
 
 extern "C" int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream) {
   if (!h) return QOC_EINVAL;
   if (!x_dev || !FG_dev) { h->err = "qoc_eval_allreduce_device: null pointer"; return QOC_EINVAL; }
-  if (!h->system_set) { h->err = "qoc_eval_allreduce_device: qoc_set_system has not been called"; return QOC_EINVAL; }
-  if (h->comm_world < 1) { h->err = "qoc_eval_allreduce_device: qoc_comm_connect has not been called"; return QOC_EINVAL; }
+  int rc = allreduce_ready(h, "qoc_eval_allreduce_device");
+  if (rc != QOC_OK) return rc;
   QOC_CUDA(h, cudaSetDevice(h->d.device));
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned long long epoch = ++h->comm_epoch;
-  double* mine = reinterpret_cast<double*>(h->comm_local) + (size_t)(epoch & 1) * h->comm_n;
-  if (!want_gradient) QOC_CUDA(h, cudaMemsetAsync(mine, 0, h->comm_n * sizeof(double), st));   // G part undefined otherwise
-  int rc = eval_device_on(h, x_dev, mine, want_gradient, st);
+  const int gi = want_gradient ? 1 : 0;
+  if (h->path == 1 && h->use_graph) {       // replay a graph captured for this (x_dev, FG_dev) pair on the caller's stream
+    if (h->ard_graph[gi] && (h->ard_x[gi] != x_dev || h->ard_fg[gi] != FG_dev)) { cudaGraphExecDestroy(h->ard_graph[gi]); h->ard_graph[gi] = nullptr; }
+    if (!h->ard_graph[gi]) {
+      const bool ok = capture_graph(h, &h->ard_graph[gi], &h->ard_launches[gi], [&]() { return enqueue_allreduce(h, x_dev, FG_dev, want_gradient, h->stream) == QOC_OK; });
+      h->st.n_evals--;
+      if (ok) { h->ard_x[gi] = x_dev; h->ard_fg[gi] = FG_dev; }
+      else { h->use_graph = false; h->in_capture = false; }
+    }
+    if (h->ard_graph[gi]) {
+      QOC_CUDA(h, cudaGraphLaunch(h->ard_graph[gi], st));
+      h->st.n_evals++; h->st.n_launches += h->ard_launches[gi]; h->st.launches_last_eval = h->ard_launches[gi];
+      return QOC_OK;
+    }
+  }
+  return enqueue_allreduce(h, x_dev, FG_dev, want_gradient, st);
+}
+
+// Host-buffer variant: every rank passes the same pulse(s) and receives the summed F, G.
+extern "C" int qoc_eval_allreduce(qoc_handle* h, const double* x, double* F, double* G) {
+  if (!h) return QOC_EINVAL;
+  if (!x) { h->err = "qoc_eval_allreduce: null pulse"; return QOC_EINVAL; }
+  int rc = allreduce_ready(h, "qoc_eval_allreduce");
   if (rc != QOC_OK) return rc;
-  const int blocks = (int)std::min<size_t>((h->comm_n + 255) / 256, 64);
-  oneshot_allreduce_kernel<<<blocks, 256, 0, st>>>(h->comm_peers, h->comm_world, h->comm_rank, epoch, h->comm_n, FG_dev);
-  return launch_check(h, "oneshot_allreduce_kernel");
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  const size_t nx = (size_t)h->d.R * h->NK;
+  const bool grad = G != nullptr;
+  const int gi = grad ? 1 : 0;
+  memcpy(h->hx, x, nx * sizeof(double));
+  bool done = false;
+  if (h->path == 1 && h->use_graph) {
+    if (!h->ar_graph[gi]) {
+      const bool ok = capture_graph(h, &h->ar_graph[gi], &h->ar_launches[gi], [&]() {
+        bool k = cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream) == cudaSuccess;
+        k = k && enqueue_allreduce(h, h->x, h->out, grad, h->stream) == QOC_OK;
+        return k && copy_result_async(h, grad) == cudaSuccess;
+      });
+      h->st.n_evals--;
+      if (!ok) { h->use_graph = false; h->in_capture = false; }
+    }
+    if (h->ar_graph[gi]) {
+      QOC_CUDA(h, cudaGraphLaunch(h->ar_graph[gi], h->stream));
+      h->st.n_evals++; h->st.n_launches += h->ar_launches[gi]; h->st.launches_last_eval = h->ar_launches[gi];
+      QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+      done = true;
+    }
+  }
+  if (!done) {
+    QOC_CUDA(h, cudaMemcpyAsync(h->x, h->hx, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = enqueue_allreduce(h, h->x, h->out, grad, h->stream)) != QOC_OK) return rc;
+    QOC_CUDA(h, copy_result_async(h, grad));
+    QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  unpack_result(h, h->hout, F, G);
+  return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single-process multi-device
+// A handle created with qoc_desc.n_devices > 1 owns one ordinary sub-handle per device, each holding a contiguous block of
+// the ensemble members (the serial member loop of src/solve.jl:166 cut into blocks).  One evaluation = one CUDA graph that
+// spans the devices: fork from the lead stream, per device H2D(x) -> chain kernels -> member reduction, join, the lead
+// device sums the weighted partial rows in fixed device order (peer-memory loads over NVLink, or staged peer copies when
+// peer access is unavailable), penalties, one D2H.  No inter-process plumbing, no flags: stream events order everything.
+struct MultiState {
+  int n = 0;
+  std::vector<int> dev, m_lo;               // device ordinal and first member of every shard (m_lo has n + 1 entries)
+  std::vector<qoc_handle*> sub;
+  std::vector<cudaEvent_t> ev_done;
+  cudaEvent_t ev_fork = nullptr;
+  double *hx = nullptr, *hout = nullptr;    // pinned, portable
+  double *total = nullptr, *x0 = nullptr;   // lead device: summed rows; the pulse (for the penalty kernel)
+  const double** parts = nullptr;           // lead device: pointers to the shards' partial rows
+  std::vector<double*> stage;               // lead-device copies of the partial rows when peer access is unavailable
+  bool peer = true, use_graph = true;
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  int graph_launches[2] = {0, 0};
+};
+
+__global__ void multi_sum_kernel(const double* const* __restrict__ parts, int n, size_t len, double* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < n; r++) s += parts[r][i];       // fixed device order: reproducible
+    out[i] = s;
+  }
+}
+
+static void multi_drop_graphs(qoc_handle* h) {
+  if (!h->multi) return;
+  for (auto& g : h->multi->graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+}
+
+static void multi_destroy(qoc_handle* h) {
+  MultiState* m = h->multi;
+  if (!m) return;
+  if (!m->sub.empty() && m->sub[0]) { cudaSetDevice(m->dev[0]); cudaStreamSynchronize(m->sub[0]->stream); }
+  multi_drop_graphs(h);
+  for (qoc_handle* sh : m->sub) if (sh) qoc_destroy(sh);
+  if (m->n > 0) cudaSetDevice(m->dev[0]);
+  for (cudaEvent_t e : m->ev_done) if (e) cudaEventDestroy(e);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (double* p : m->stage) if (p) cudaFree(p);
+  if (m->total) cudaFree(m->total);
+  if (m->x0) cudaFree(m->x0);
+  if (m->parts) cudaFree((void*)m->parts);
+  if (m->hx) cudaFreeHost(m->hx);
+  if (m->hout) cudaFreeHost(m->hout);
+  delete m;
+  h->multi = nullptr;
+}
+
+static int multi_create(qoc_handle** out, const qoc_desc& d, int ndev) {
+  if (d.n_devices > QOC_MAX_DEVICES) { g_create_error = "qoc_create: n_devices exceeds QOC_MAX_DEVICES"; return QOC_EINVAL; }
+  const int n = std::min(d.n_devices, d.M);            // every shard needs at least one member
+  for (int i = 0; i < n; i++) {
+    if (d.device_ids[i] < 0 || d.device_ids[i] >= ndev) { g_create_error = "qoc_create: bad device ordinal in device_ids"; return QOC_EINVAL; }
+  }
+  qoc_handle* h = new qoc_handle();
+  MultiState* m = new MultiState();
+  h->multi = m; h->d = d; h->d.device = d.device_ids[0];
+  if (h->d.expm_theta <= 0) h->d.expm_theta = T8_THETA_DEFAULT;
+  h->NK = d.N * d.K;
+  m->n = n;
+  auto fail = [&](int rc, const std::string& msg) { g_create_error = msg; multi_destroy(h); delete h; return rc; };
+  auto cfail = [&](cudaError_t e, const char* what) { return fail(e == cudaErrorMemoryAllocation ? QOC_ENOMEM : QOC_ECUDA, std::string(what) + ": " + cudaGetErrorString(e)); };
+  m->sub.assign(n, nullptr); m->ev_done.assign(n, nullptr); m->stage.assign(n, nullptr);
+  for (int r = 0; r <= n; r++) m->m_lo.push_back((int)((long)r * d.M / n));
+  for (int r = 0; r < n; r++) {
+    m->dev.push_back(d.device_ids[r]);
+    qoc_desc sd = d;
+    sd.n_devices = 0; sd.device = d.device_ids[r]; sd.M = m->m_lo[r + 1] - m->m_lo[r];
+    int rc = qoc_create(&m->sub[r], &sd);
+    if (rc != QOC_OK) return fail(rc, "qoc_create (device " + std::to_string(sd.device) + "): " + g_create_error);
+    m->sub[r]->is_sub = true;
+    if (m->sub[r]->path != 1) m->use_graph = false;     // the D > 16 pipeline synchronises its stream once per evaluation
+  }
+  if (const char* e = getenv("QOC_GRAPH")) m->use_graph = m->use_graph && atoi(e) != 0;
+  cudaError_t ce;
+  const size_t rowlen = (size_t)d.R * (h->NK + 1);
+  if ((ce = cudaSetDevice(m->dev[0])) != cudaSuccess) return cfail(ce, "cudaSetDevice");
+  for (int r = 1; r < n; r++) {                         // lead device reads the other shards' rows through peer memory
+    if (m->dev[r] == m->dev[0]) continue;               // a repeated ordinal (two shards on one device) needs no peer mapping
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, m->dev[0], m->dev[r]);
+    if (can) { ce = cudaDeviceEnablePeerAccess(m->dev[r], 0); if (ce == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ce = cudaSuccess; } }
+    if (!can || ce != cudaSuccess) { cudaGetLastError(); m->peer = false; }
+  }
+  if (const char* e = getenv("QOC_MULTI_PEER")) m->peer = m->peer && atoi(e) != 0;      // A/B: force the staged-copy path
+  if ((ce = cudaHostAlloc((void**)&m->hx, (size_t)d.R * std::max(h->NK, 1) * sizeof(double), cudaHostAllocPortable)) != cudaSuccess) return cfail(ce, "cudaHostAlloc");
+  if ((ce = cudaHostAlloc((void**)&m->hout, rowlen * sizeof(double), cudaHostAllocPortable)) != cudaSuccess) return cfail(ce, "cudaHostAlloc");
+  if ((ce = cudaMalloc((void**)&m->total, rowlen * sizeof(double))) != cudaSuccess) return cfail(ce, "cudaMalloc");
+  if ((ce = cudaMalloc((void**)&m->parts, n * sizeof(double*))) != cudaSuccess) return cfail(ce, "cudaMalloc");
+  std::vector<const double*> pp(n);
+  for (int r = 0; r < n; r++) {
+    pp[r] = m->sub[r]->out;
+    if (!m->peer && r > 0) {
+      if ((ce = cudaMalloc((void**)&m->stage[r], rowlen * sizeof(double))) != cudaSuccess) return cfail(ce, "cudaMalloc");
+      pp[r] = m->stage[r];
+    }
+  }
+  for (int r = 0; r < n; r++) {                         // an event is recorded on streams of the device it was created on
+    cudaSetDevice(m->dev[r]);
+    if ((ce = cudaEventCreateWithFlags(&m->ev_done[r], cudaEventDisableTiming)) != cudaSuccess) return cfail(ce, "cudaEventCreate");
+  }
+  cudaSetDevice(m->dev[0]);
+  if ((ce = cudaMemcpy((void*)m->parts, pp.data(), n * sizeof(double*), cudaMemcpyHostToDevice)) != cudaSuccess) return cfail(ce, "cudaMemcpy");
+  if ((ce = cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return cfail(ce, "cudaEventCreate");
+  h->path = m->sub[0]->path;
+  *out = h;
+  return QOC_OK;
+}
+
+static int multi_set_system(qoc_handle* h, const double* A, const double* B, const double* Xi, const double* Xt, const double* wts, int shared_flags) {
+  MultiState* m = h->multi;
+  const size_t DD2 = 2 * (size_t)h->d.D * h->d.D;     // doubles per matrix
+  const int K = h->d.K;
+  cudaSetDevice(m->dev[0]);
+  cudaStreamSynchronize(m->sub[0]->stream);
+  multi_drop_graphs(h);
+  for (int r = 0; r < m->n; r++) {
+    const size_t lo = (size_t)m->m_lo[r];
+    int rc = qoc_set_system(m->sub[r], (shared_flags & QOC_SHARED_A) ? A : A + lo * DD2, (!B || (shared_flags & QOC_SHARED_B)) ? B : B + lo * K * DD2,
+                            (shared_flags & QOC_SHARED_XI) ? Xi : Xi + lo * DD2, (shared_flags & QOC_SHARED_XT) ? Xt : Xt + lo * DD2,
+                            wts ? wts + lo : nullptr, shared_flags);
+    if (rc != QOC_OK) { h->err = "device " + std::to_string(m->dev[r]) + ": " + m->sub[r]->err; return rc; }
+  }
+  h->system_set = true;
+  return QOC_OK;
+}
+
+// everything one evaluation enqueues, forked from and joined into the lead stream (capturable)
+static int multi_enqueue(qoc_handle* h, bool grad) {
+  MultiState* m = h->multi;
+  const qoc_desc& d = h->d;
+  const size_t nx = (size_t)d.R * h->NK, rowlen = (size_t)d.R * (h->NK + 1);
+  cudaStream_t lead = m->sub[0]->stream;
+  QOC_CUDA(h, cudaSetDevice(m->dev[0]));
+  QOC_CUDA(h, cudaEventRecord(m->ev_fork, lead));
+  for (int r = 0; r < m->n; r++) {
+    qoc_handle* sh = m->sub[r];
+    QOC_CUDA(h, cudaSetDevice(m->dev[r]));
+    if (r > 0) QOC_CUDA(h, cudaStreamWaitEvent(sh->stream, m->ev_fork, 0));
+    QOC_CUDA(h, cudaMemcpyAsync(sh->x, m->hx, nx * sizeof(double), cudaMemcpyHostToDevice, sh->stream));
+    int rc = eval_core(sh, sh->x, sh->out, grad, sh->stream);
+    if (rc != QOC_OK) { h->err = "device " + std::to_string(m->dev[r]) + ": " + sh->err; return rc; }
+    if (r > 0) {
+      if (!m->peer) QOC_CUDA(h, cudaMemcpyPeerAsync(m->stage[r], m->dev[0], sh->out, m->dev[r], rowlen * sizeof(double), sh->stream));
+      QOC_CUDA(h, cudaEventRecord(m->ev_done[r], sh->stream));
+    }
+  }
+  QOC_CUDA(h, cudaSetDevice(m->dev[0]));
+  for (int r = 1; r < m->n; r++) QOC_CUDA(h, cudaStreamWaitEvent(lead, m->ev_done[r], 0));
+  multi_sum_kernel<<<(unsigned)std::min<size_t>((rowlen + 255) / 256, 296), 256, 0, lead>>>(m->parts, m->n, rowlen, m->total);
+  { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { h->err = std::string("multi_sum_kernel: ") + cudaGetErrorString(e); return QOC_ECUDA; } }
+  if (h->pen_amp != 0.0 || h->pen_var != 0.0) {
+    penalty_kernel<<<d.R, 256, 0, lead>>>(m->sub[0]->x, m->total, d.N, d.K, h->pen_amp, h->pen_var, grad ? 1 : 0);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { h->err = std::string("penalty_kernel: ") + cudaGetErrorString(e); return QOC_ECUDA; }
+  }
+  const size_t row = (size_t)h->NK + 1;
+  if (grad) QOC_CUDA(h, cudaMemcpyAsync(m->hout, m->total, rowlen * sizeof(double), cudaMemcpyDeviceToHost, lead));
+  else QOC_CUDA(h, cudaMemcpy2DAsync(m->hout, row * sizeof(double), m->total, row * sizeof(double), sizeof(double), d.R, cudaMemcpyDeviceToHost, lead));
+  return QOC_OK;
+}
+
+static int multi_eval(qoc_handle* h, const double* x, double* F, double* G) {
+  MultiState* m = h->multi;
+  const bool grad = G != nullptr;
+  const int gi = grad ? 1 : 0;
+  memcpy(m->hx, x, (size_t)h->d.R * h->NK * sizeof(double));
+  cudaStream_t lead = m->sub[0]->stream;
+  bool done = false;
+  if (m->use_graph) {
+    if (!m->graph[gi]) {
+      QOC_CUDA(h, cudaSetDevice(m->dev[0]));
+      bool ok = cudaStreamBeginCapture(lead, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        std::vector<long long> before(m->n);
+        for (int r = 0; r < m->n; r++) { m->sub[r]->in_capture = true; before[r] = m->sub[r]->st.n_launches; }
+        const int rc = multi_enqueue(h, grad);
+        int launches = 1 + ((h->pen_amp != 0.0 || h->pen_var != 0.0) ? 1 : 0);
+        for (int r = 0; r < m->n; r++) {
+          qoc_handle* sh = m->sub[r];
+          sh->in_capture = false; launches += (int)(sh->st.n_launches - before[r]); sh->st.n_launches = before[r]; sh->st.n_evals--;
+        }
+        cudaSetDevice(m->dev[0]);
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(lead, &graph);
+        ok = rc == QOC_OK && e == cudaSuccess && graph;
+        if (ok) ok = cudaGraphInstantiate(&m->graph[gi], graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (ok) m->graph_launches[gi] = launches; else { m->graph[gi] = nullptr; cudaGetLastError(); }
+      } else cudaGetLastError();
+      if (!ok) m->use_graph = false;
+    }
+    if (m->graph[gi]) {
+      QOC_CUDA(h, cudaSetDevice(m->dev[0]));
+      QOC_CUDA(h, cudaGraphLaunch(m->graph[gi], lead));
+      QOC_CUDA(h, cudaStreamSynchronize(lead));
+      h->st.n_launches += m->graph_launches[gi]; h->st.launches_last_eval = m->graph_launches[gi];
+      done = true;
+    }
+  }
+  if (!done) {
+    long long before = 0, after = 0;
+    for (qoc_handle* sh : m->sub) before += sh->st.n_launches;
+    int rc = multi_enqueue(h, grad);
+    if (rc != QOC_OK) return rc;
+    QOC_CUDA(h, cudaSetDevice(m->dev[0]));
+    QOC_CUDA(h, cudaStreamSynchronize(lead));
+    for (qoc_handle* sh : m->sub) after += sh->st.n_launches;
+    h->st.launches_last_eval = (int)(after - before) + 1; h->st.n_launches += h->st.launches_last_eval;
+  }
+  h->st.n_evals++;
+  unpack_result(h, m->hout, F, G);
+  return QOC_OK;
+}
+
+static void multi_stats(qoc_handle* h) {
+  MultiState* m = h->multi;
+  long long ws = 0;
+  for (qoc_handle* sh : m->sub) { qoc_stats s; qoc_get_stats(sh, &s); ws += s.workspace_bytes; }
+  h->st.workspace_bytes = ws;
+  h->st.path = m->sub[0]->st.path;
+  h->st.gpu_ms_last_eval = 0.f; h->st.main_kernel_ms_avg = 0.f; h->st.main_kernel_samples = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ L-BFGS
@@ -859,6 +1277,7 @@ extern "C" int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbf
 
 extern "C" int qoc_get_stats(qoc_handle* h, qoc_stats* out) {
   if (!h || !out) return QOC_EINVAL;
+  if (h->multi) { multi_stats(h); *out = h->st; return QOC_OK; }
   h->st.workspace_bytes = h->ws_bytes + (h->big ? big_workspace(h->big) : 0);
   {  // average over the event pairs recorded since the previous qoc_get_stats (at most KRING)
     int n = h->kring_count < qoc_handle::KRING ? h->kring_count : qoc_handle::KRING;

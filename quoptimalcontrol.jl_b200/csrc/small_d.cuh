@@ -21,43 +21,9 @@ constexpr double T8_X5 = 0.16112557339541759283;
 constexpr double T8_X6 = 0.014090917158378207731;
 constexpr double T8_X7 = 0.033792797010870504141;
 constexpr double T8_Y2 = 0.13549236135285063166;
-// ||A||_1 <= theta  =>  ||A||^9/9! * e^||A|| <= 2^-53
-constexpr double T8_THETA_DEFAULT = 0.0694;
 
-enum { SYS_DENSITY = 0, SYS_UNITARY = 1 };
-enum { GRAD_NONE = 0, GRAD_FIRST = 1, GRAD_EXACT = 2 };
 
-struct SmallParams {
-  int D, N, K, M, R;
-  int pack_mode;       // 0: members packed in a warp (same pulse); 1: pulses packed (same member)
-  int n_groups;        // warps of work
-  int n_inner;         // pack_mode 0: ceil(M/CPW) member groups per pulse; pack_mode 1: M
-  int nmat;            // packed system matrices per system group: 1 + K (+ K transposed controls if exact)
-  int sys_in_smem;
-  int have_P;          // propagators were precomputed into storeP by expm_slices_kernel
-  int sign_static;     // first-order UnitaryGate: +1 grad_func! (in-place), -1 grad_func (static)
-  int fom_exact;       // figure of merit of the exact (ADGRAPE / C1) functional even when no gradient is asked
-  int herm;            // drift and all controls are Hermitian (host-checked): generator is anti-Hermitian
-  double dt, theta;
-  const double2* sys;  // [n_sysgroups][nmat][NB*NB*2*32], pre-multiplied by -i*dt
-  const double2* xi;   // [n_sysgroups][NB*NB*2*32]; UnitaryGate: packed transposed (the chain runs on S^T)
-  const double2* xt;
-  const double* x;     // [R][N][K]  (= the reference's K x N column-major control_array per pulse)
-  double2* storeP;     // [n_groups][N][NB*NB*2*32]
-  double2* storeS;     // [n_groups][N][NB*NB*2*32]
-  double* fomc;        // [R][M]
-  double* gradc;       // [R][M][N][K]
-  double2* out_final;  // optional [R][M][D*D]: final forward state, column-major complex
-  // chunk-parallel fused mode (Cn > 1): warp (w, c) handles slices [c*N/Cn, (c+1)*N/Cn) of group w, starting from
-  // the boundary state bS[w][c] and boundary costate bC[w][c+1]; overlaps come from tau_in (boundary2_kernel)
-  int Cn;
-  const double2* bS;   // [n_groups][Cn+1][E]
-  const double2* bC;   // [n_groups][Cn+1][E]
-  const double* tau_in;  // [n_groups][CPW][2]
-  const double2* ident;  // packed identity (closed-system kernel)
-};
 
-template <int NB> __host__ __device__ constexpr int cm_elems() { return NB * NB * 2 * 32; }  // double2 per packed matrix
 
 // 1-norm upper bound (column sums of |re|+|im|), warp-uniform max over all packed chains; float is enough
 // for a scaling decision and is rounded up.
@@ -488,16 +454,6 @@ __global__ void __launch_bounds__(128, NB == 1 ? QOC_CHAIN_MINB : 1) chain_unita
 // Slice-parallel propagators: one warp per (system group / pulse, slice).  Writes the packed TRANSPOSED
 // propagator used by chain_kernel (storeP) and/or the caller's column-major layout
 // (pw_prop_save!, timeevolution.jl:98-110).
-struct SliceParams {
-  int D, N, K, M, R, pack_mode, n_groups, n_inner, nmat, herm;
-  double dt, theta;
-  const double2* sys;
-  const double* x;
-  double2* storeP;     // optional packed [n_groups][N][E]: TRANSPOSED result
-  double2* storeP2;    // optional packed [n_groups][N][E]: result as is
-  double2* out_user;   // optional [R][M][N][D*D] column-major complex
-  int mode;            // 0: propagator exp(-i dt H); 1: Hamiltonian H (pw_ham_save!); 2: generator -i dt H (pw_gen_save!)
-};
 template <int NB, int CPW>
 __global__ void __launch_bounds__(128) expm_slices_kernel(const SliceParams p) {
   extern __shared__ double2 smem[];
@@ -521,88 +477,6 @@ __global__ void __launch_bounds__(128) expm_slices_kernel(const SliceParams p) {
       int row, col; chain_coords<NB, CPW>(L, i, j, e, p.D, row, col);
       if (sl.valid && row >= 0) o[(size_t)col * p.D + row] = make_double2(out.re[i][j][e], out.im[i][j][e]);
     }
-  }
-}
-
-// Pack caller matrices (column-major complex D x D) into the warp layout.  One thread per packed double2.
-//   dst[(og*nmat_dst + mat_dst)*E + ((i*NB+j)*2+ri)*32 + lane] ; slot s of group og reads source matrix
-//   src + src_index(og, s)*src_stride, transposed if asked; everything outside the chain's D x D block is 0.
-struct PackParams {
-  int D, NB, CPW, n_og, nmat_dst, mat_dst, transpose;
-  int pack_mode;      // 0: slot s -> member og*CPW+s (clamped to n_src-1); 1: every slot -> member og
-  int n_src;          // number of distinct source matrices (1 if shared)
-  long src_stride;    // in double2 between consecutive source members (0 if shared)
-  double scale_re, scale_im;   // every element is multiplied by this complex factor (-i*dt for A, B)
-  const double2* src;
-  double2* dst;
-};
-__global__ void pack_kernel(const PackParams p) {
-  const int E = p.NB * p.NB * 2 * 32;
-  long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= (long)p.n_og * E) return;
-  int og = (int)(tid / E), rem = (int)(tid - (long)og * E);
-  int lane = rem & 31, ri = (rem >> 5) & 1, blk = rem >> 6;
-  int i = blk / p.NB, j = blk - i * p.NB;
-  int g = lane >> 2, q = lane & 3;
-  int DPc = 8 * p.NB / p.CPW;
-  double v[2];
-  for (int e = 0; e < 2; e++) {
-    int row = 8 * i + g, col = 8 * j + 2 * q + e;
-    int s = row / DPc;
-    int rr = row - s * DPc, cc = col - s * DPc;
-    double val = 0.0;
-    if (cc >= 0 && cc < DPc && rr < p.D && cc < p.D) {
-      long member = p.pack_mode == 0 ? (long)og * p.CPW + s : og;
-      if (member > p.n_src - 1) member = p.n_src - 1;
-      const double2* m = p.src + member * p.src_stride;
-      double2 z = p.transpose ? m[(size_t)rr * p.D + cc] : m[(size_t)cc * p.D + rr];
-      val = ri ? (p.scale_re * z.y + p.scale_im * z.x) : (p.scale_re * z.x - p.scale_im * z.y);
-    }
-    v[e] = val;
-  }
-  p.dst[((size_t)og * p.nmat_dst + p.mat_dst) * E + rem] = make_double2(v[0], v[1]);
-}
-
-// Deterministic weighted ensemble reduction  F[r] = sum_k w_k fom[r,k],  G[r,:] = sum_k w_k grad[r,k,:]
-// (/root/reference/src/solve.jl:171-191), two fixed-order passes: pass 1 folds `chunk` consecutive members (k ascending)
-// into one of at most RED_MAX_CHUNKS partial rows, pass 2 folds the partial rows (8 interleaved lanes per element, then a
-// fixed-order combine).  With a single chunk pass 1 writes the result itself (part == out, no pass 2).
-constexpr int RED_MAX_CHUNKS = 128, RED_LANES = 8;
-__global__ void reduce_members_pass1(const double* __restrict__ gradc, const double* __restrict__ fomc,
-                                     const double* __restrict__ wts, double* __restrict__ part,
-                                     int M, int NK, int chunk, int nchunks) {
-  // grid: (ceil((NK+1)/256) * R, nchunks); part[r][chunk][NK+1] (entry 0 = fom)
-  const int bpr = (NK + 1 + blockDim.x - 1) / blockDim.x;
-  int r = blockIdx.x / bpr;
-  int e = (blockIdx.x - r * bpr) * blockDim.x + threadIdx.x;
-  if (e > NK) return;
-  int ch = blockIdx.y;
-  int k0 = ch * chunk, k1 = min(M, k0 + chunk);
-  double s = 0.0;
-  if (e == 0) { for (int k = k0; k < k1; k++) s += wts[k] * fomc[(size_t)r * M + k]; }
-  else if (gradc) {
-    const double* g = gradc + (size_t)r * M * NK + (e - 1);
-#pragma unroll 4
-    for (int k = k0; k < k1; k++) s += wts[k] * __ldg(g + (size_t)k * NK);
-  }
-  part[((size_t)r * nchunks + ch) * (NK + 1) + e] = s;
-}
-__global__ void __launch_bounds__(32 * RED_LANES) reduce_members_pass2(const double* __restrict__ part, double* __restrict__ out, int NK, int nchunks) {
-  // block: 32 elements x RED_LANES partial-row lanes; grid: ceil((NK+1)/32) * R
-  __shared__ double sm[RED_LANES][33];
-  const int bpr = (NK + 1 + 31) / 32;
-  const int r = blockIdx.x / bpr;
-  const int e = (blockIdx.x - r * bpr) * 32 + (threadIdx.x & 31), lane = threadIdx.x >> 5;
-  double s = 0.0;
-  if (e <= NK)
-    for (int ch = lane; ch < nchunks; ch += RED_LANES) s += part[((size_t)r * nchunks + ch) * (NK + 1) + e];
-  sm[lane][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (lane == 0 && e <= NK) {
-    double t = sm[0][threadIdx.x];
-#pragma unroll
-    for (int l = 1; l < RED_LANES; l++) t += sm[l][threadIdx.x];
-    out[(size_t)r * (NK + 1) + e] = t;
   }
 }
 

@@ -22,30 +22,7 @@
 
 namespace qoc {
 
-struct PhasedParams {
-  int D, N, K, M, R, pack_mode, n_groups, n_inner, nmat, herm, Cn;
-  int sign_static, fom_exact;
-  double theta;
-  const double2* sys;      // packed, pre-multiplied by -i dt
-  const double2* xi;       // packed (unitary: transposed)
-  const double2* xt;
-  const double* x;
-  double2* storePt;        // [n_groups][N][E]   P_t^T
-  double2* storeP;         // [n_groups][N][E]   P_t
-  double2* stS;            // [n_groups][N+1][E] unitary: S_t^T, density: S_t
-  double2* stC;            // [n_groups][N+1][E] unitary: C_t^T, density: C_t   (C_N = Xt)
-  double2* totT;           // [n_groups][Cn][E]  T_c
-  double2* totTt;          // [n_groups][Cn][E]  T_c^T
-  double* tau;             // [n_groups][CPW][2] overlap per chain (written by the forward sweep)
-  double2* bS;             // [n_groups][Cn+1][E] chunk-boundary states   (chunk-parallel fused mode)
-  double2* bC;             // [n_groups][Cn+1][E] chunk-boundary costates
-  int sys_in_smem;
-  int store_plain;         // chunk_expm_kernel stores P_t instead of P_t^T (closed-system mode)
-  double* fomc;
-  double* gradc;
-};
 
-__device__ __forceinline__ int chunk_lo(int c, int N, int Cn) { return (int)((long)c * N / Cn); }
 
 // B1: chunk-total propagators.  T <- T * P_t for t descending: nt(T, Pt) = T * (P_t^T)^T, no transposes needed.
 template <int NB, int CPW>

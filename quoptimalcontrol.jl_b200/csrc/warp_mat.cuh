@@ -12,11 +12,11 @@
 // (2 STS.128 + 4 LDS.64 per complex 8x8 block, bank-conflict free, no selects).
 #pragma once
 #include <cuda_runtime.h>
+#include "params.h"
 
 namespace qoc {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
-constexpr int TB_PLANE = 80;   // doubles per real 8x8 plane in the transpose tile: 8 rows x stride 10
 
 template <int NB> struct CM { double re[NB][NB][2]; double im[NB][NB][2]; };
 

@@ -23,7 +23,10 @@ class GrapeEvaluator:
     x has shape (K, N) like the reference's control_array, or (R, K, N) for a multi-start batch."""
 
     def __init__(self, members, T, n_slices, sys_type, wts=None, gradient="first_order",
-                 convention="inplace", n_pulses=1, device=0, expm_theta=0.0, pure_state=True):
+                 convention="inplace", n_pulses=1, device=0, expm_theta=0.0, pure_state=True, devices=None,
+                 penalty=(0.0, 0.0)):
+        """devices: list of CUDA ordinals -> single-process multi-device handle (members block-sharded over them);
+        penalty: (w_amp, w_var) weights of the C3 / C4 control penalties (src/cost_functions.jl:29-39)."""
         self._h = C.c_void_p()
         self._lib = _lib.load()
         M = len(members)
@@ -37,6 +40,14 @@ class GrapeEvaluator:
                             convention={"inplace": _lib.REF_INPLACE, "static": _lib.REF_STATIC}[convention],
                             device=int(device), expm_theta=float(expm_theta),
                             flags=0 if pure_state else _lib.QOC_FLAG_NO_PURE_STATE)
+        if devices is not None and len(devices) > 1:
+            if len(devices) > _lib.MAX_DEVICES:
+                raise ValueError(f"at most {_lib.MAX_DEVICES} devices")
+            desc.n_devices = len(devices)
+            for i, dv in enumerate(devices):
+                desc.device_ids[i] = int(dv)
+        elif devices is not None and len(devices) == 1:
+            desc.device = int(devices[0])
         rc = self._lib.qoc_create(C.byref(self._h), C.byref(desc))
         if rc != _lib.QOC_OK:
             msg = self._lib.qoc_last_error(None).decode()
@@ -51,6 +62,8 @@ class GrapeEvaluator:
             raise ValueError("wts must have one weight per member")
         self._check(self._lib.qoc_set_system(self._h, A.ctypes.data, B.ctypes.data, Xi.ctypes.data, Xt.ctypes.data,
                                              None if w is None else w.ctypes.data, 0))
+        if penalty[0] or penalty[1]:
+            self.set_penalty(*penalty)
 
     # ------------------------------------------------------------------ helpers
     def _check(self, rc):
@@ -73,6 +86,28 @@ class GrapeEvaluator:
         F = np.empty(self.R)
         G = np.empty((self.R, self.N, self.K)) if want_grad else None
         self._check(self._lib.qoc_eval(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
+        Gk = None if G is None else np.swapaxes(G, 1, 2)
+        if single:
+            return float(F[0]), (None if Gk is None else np.ascontiguousarray(Gk[0]))
+        return F, Gk
+
+    def set_penalty(self, w_amp=0.0, w_var=0.0):
+        """F += w_amp*C3(x) + w_var*C4(x) (and the gradient) on every following evaluation."""
+        self._check(self._lib.qoc_set_penalty(self._h, float(w_amp), float(w_var)))
+
+    def eval_values(self, xs):
+        """Fidelity-only evaluation of a batch of candidate pulses xs[R, K, N] in one call (gradient-free callers:
+        a Nelder-Mead simplex, dCRAB candidates).  Returns F[R]."""
+        F, _ = self.eval(xs, want_grad=False)
+        return np.atleast_1d(F)
+
+    def eval_allreduce(self, x, want_grad=True):
+        """Like eval(), through qoc_eval_allreduce: every rank passes the same x and gets the sum over all ranks."""
+        single = np.asarray(x).ndim == 2
+        xb = self._pack_x(x)
+        F = np.empty(self.R)
+        G = np.empty((self.R, self.N, self.K)) if want_grad else None
+        self._check(self._lib.qoc_eval_allreduce(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
         Gk = None if G is None else np.swapaxes(G, 1, 2)
         if single:
             return float(F[0]), (None if Gk is None else np.ascontiguousarray(Gk[0]))
