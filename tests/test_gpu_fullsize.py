@@ -153,7 +153,8 @@ def test_second_set_system_drops_captured_graph():
         ev._check(ev._lib.qoc_set_system(ev._h, a.ctypes.data, b.ctypes.data, xi.ctypes.data, xt.ctypes.data, None, 0))
         F, G = ev.eval(x)
         assert_parity(F, G, *orc.fom_and_gradient_grape(nonh[0], nonh[1], x, T, nonh[2], nonh[3], orc.STATE_TRANSFER))
-        ev._check(ev._lib.qoc_set_system(ev._h, cm(herm[0]).ctypes.data, cm(herm[1]).ctypes.data, cm(herm[2]).ctypes.data, cm(herm[3]).ctypes.data, None, 0))
+        a, b, xi, xt = cm(herm[0]), cm(herm[1]), cm(herm[2]), cm(herm[3])          # keep the buffers alive across the call
+        ev._check(ev._lib.qoc_set_system(ev._h, a.ctypes.data, b.ctypes.data, xi.ctypes.data, xt.ctypes.data, None, 0))
         F, G = ev.eval(x)
         assert_parity(F, G, *orc.fom_and_gradient_grape(herm[0], herm[1], x, T, herm[2], herm[3], orc.STATE_TRANSFER))
 
