@@ -46,6 +46,8 @@ phased_fn pick_sweep_unitary(int NB, int CPW) {
   return sweep_unitary_kernel<1, 1>;
 }
 
+phased_fn pick_sweep_unitary_dmma() { return sweep_unitary_dmma_kernel; }
+int sweep_unitary_dmma_smem() { return (1024 + 4 * 8 * DOT_LD) * (int)sizeof(double); }
 bal_fn pick_bal_expm(int NB, int CPW) {
   if (NB == 2) return bal_expm_kernel<2, 1>;
   if (CPW == 4) return bal_expm_kernel<1, 4>;

@@ -116,6 +116,8 @@ phased_fn pick_chunk_expm(int NB, int CPW);
 phased_fn pick_boundary2(int NB, int CPW, int sys);
 phased_fn pick_boundary_unitary(int NB, int CPW, int sys);
 phased_fn pick_sweep_unitary(int NB, int CPW);
+phased_fn pick_sweep_unitary_dmma();     // D = 5..8 (NB = 1, one chain per warp), K <= 8: trace-dots on the tensor pipe
+int sweep_unitary_dmma_smem();           // its dynamic shared memory per CTA; grid = chains x ceil(Cn / 4)
 typedef void (*bal_fn)(const PhasedParams, const BalTables);
 bal_fn pick_bal_expm(int NB, int CPW);
 bal_fn pick_bal_boundary(int NB, int CPW, int sys);

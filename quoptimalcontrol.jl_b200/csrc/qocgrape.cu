@@ -520,6 +520,10 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
     const int sweep_in_smem = bbytes <= 96 * 1024;
     const int smem3 = sweep_in_smem ? (int)bbytes : 0;
     if (smem3 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    bool dots_on_dmma = h->NB == 1 && h->CPW == 1 && h->d.K <= 8 && h->d.K >= 1;
+    if (const char* e = getenv("QOC_DOTS_DMMA")) dots_on_dmma = dots_on_dmma && atoi(e) != 0;      // A/B testing
+    if (dots_on_dmma && sweep_unitary_dmma_smem() > 48 * 1024)
+      QOC_CUDA(h, cudaFuncSetAttribute((const void*)pick_sweep_unitary_dmma(), cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_unitary_dmma_smem()));
     const int parts = h->parts;
     if (parts > 1) QOC_CUDA(h, cudaEventRecord(h->ev_fork, st));
     for (int i = 0; i < parts; i++) {                       // chains [w0, w1) on their own stream: expm -> boundary -> sweep
@@ -534,8 +538,13 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
       kb<<<(unsigned)((q.w_cnt + 3) / 4), 128, h->tb_bytes, ps>>>(q);
       if ((rc = launch_check(h, "boundary_unitary_kernel")) != QOC_OK) return rc;
       q.sys_in_smem = sweep_in_smem;
-      ks<<<gchunks, 128, smem3, ps>>>(q);
-      if ((rc = launch_check(h, "sweep_unitary_kernel")) != QOC_OK) return rc;
+      if (dots_on_dmma) {
+        pick_sweep_unitary_dmma()<<<(unsigned)((long)q.w_cnt * ((h->Cn + 3) / 4)), 128, sweep_unitary_dmma_smem(), ps>>>(q);
+        if ((rc = launch_check(h, "sweep_unitary_dmma_kernel")) != QOC_OK) return rc;
+      } else {
+        ks<<<gchunks, 128, smem3, ps>>>(q);
+        if ((rc = launch_check(h, "sweep_unitary_kernel")) != QOC_OK) return rc;
+      }
       if (i > 0) QOC_CUDA(h, cudaEventRecord(h->ev_join[i], ps));
     }
     for (int i = 1; i < parts; i++) QOC_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));

@@ -395,6 +395,77 @@ __global__ void __launch_bounds__(128, NB == 1 ? QOC_SWEEP_MINB : 1) sweep_unita
   if (p.sys_in_smem) sweep_unitary_body<NB, CPW, true>(p, smem); else sweep_unitary_body<NB, CPW, false>(p, smem);
 }
 
+// K3u with the trace-dots on the tensor pipe (D = 5..8, one chain per warp, K <= 8).
+// The scalar form of emit_gradient costs 24 DFMA + a 9-stage shuffle / DADD butterfly per slice, every one of them queueing
+// for the FP64 pipe behind the other warps' DMMAs (ncu r02e: 75 % of this kernel's warp time, top stall math-pipe throttle).
+// Here W_t of 8 consecutive slices is staged in a per-warp shared-memory tile and all K x 8 dots
+//   g[c][t] = sum_f Bflat[c][f] * Wflat[t][f],   f over the 128 real entries (re plane, then im plane),
+// are one accumulated chain of 32 DMMA.8x8x4 (m = control, n = slice, k = f): the contraction over k is the cross-lane
+// reduction, the result lands as g[c = lane / 4][t = 2 (lane % 4) + {0, 1}].  Same FP64-pipe time (4 DMMA per slice), but
+// ~110 instead of ~250 instructions per slice and no dependent shuffle chain.
+//   Bd [32 k-steps][32 lanes]  control matrices in fragment order (lane (c, q) <-> Bflat[c][4 ks + q]), shared by the CTA:
+//                              the four warps of a CTA work on four chunks of the SAME chain
+//   Wb [8 slices][132]         per warp; row stride 132 doubles makes the fragment loads conflict-free
+constexpr int DOT_LD = 132;
+__global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  constexpr int NB = 1;
+  constexpr int E = cm_elems<NB>();
+  double* Bd = reinterpret_cast<double*>(smem);
+  const int warp = threadIdx.x >> 5;
+  double* Wb = Bd + 1024 + warp * (8 * DOT_LD);
+  const int Cg = (p.Cn + 3) >> 2;
+  const int wl = blockIdx.x / Cg, cg = blockIdx.x - wl * Cg;
+  const int w = p.w_off + wl, c = cg * 4 + warp;
+  const Lane L(threadIdx.x & 31);
+  const Slot<1> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  const int N = p.N, K = p.K;
+  {
+    const double* Bm = reinterpret_cast<const double*>(p.sys + (size_t)sl.sysgroup * p.nmat * E + E);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+      const int ks = i >> 5, ln = i & 31, cc = ln >> 2, q = ln & 3;
+      Bd[i] = cc < K ? Bm[(size_t)cc * (2 * E) + 4 * ks + q] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (c >= p.Cn) return;
+  const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
+  const double2* stP = p.storePt + (size_t)w * N * E;      // holds P (not P^T) in this mode
+  double* out = p.gradc + ((size_t)sl.r * p.M + sl.k) * N * K;
+  CM<NB> W = cm_load<NB>(L, p.bS + ((size_t)w * (p.Cn + 1) + c) * E);
+  CM<NB> Pn = cm_load<NB>(L, stP + (size_t)t0 * E);
+  const int cc = L.g, tq = 2 * L.q;
+  for (int tb = t0; tb < t1; tb += 8) {
+    const int nb = min(8, t1 - tb);
+    for (int i = 0; i < nb; i++) {
+      const int t = tb + i;
+      const CM<NB> P = Pn;
+      if (t + 1 < t1) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
+      double* row = Wb + i * DOT_LD + 2 * L.lane;
+      *reinterpret_cast<double2*>(row) = make_double2(W.re[0][0][0], W.re[0][0][1]);
+      *reinterpret_cast<double2*>(row + 64) = make_double2(W.im[0][0][0], W.im[0][0][1]);
+      if (t + 1 < t1) { const CM<NB> X = mul_nt<NB, true, false>(P, W); W = mul_nt<NB>(P, X); }
+    }
+    __syncwarp();
+    double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;      // four accumulator chains
+    const double* bp = Bd + L.lane;
+    const double* wp = Wb + L.g * DOT_LD + L.q;
+#pragma unroll
+    for (int ks = 0; ks < 32; ks += 4) {
+      dmma(a0, a1, bp[(ks + 0) * 32], wp[4 * (ks + 0)]);
+      dmma(b0, b1, bp[(ks + 1) * 32], wp[4 * (ks + 1)]);
+      dmma(c0, c1, bp[(ks + 2) * 32], wp[4 * (ks + 2)]);
+      dmma(d0, d1, bp[(ks + 3) * 32], wp[4 * (ks + 3)]);
+    }
+    const double g0 = (a0 + b0) + (c0 + d0), g1 = (a1 + b1) + (c1 + d1);
+    if (cc < K && sl.valid) {
+      if (tq < nb) out[(size_t)(tb + tq) * K + cc] = g0;
+      if (tq + 1 < nb) out[(size_t)(tb + tq + 1) * K + cc] = g1;
+    }
+    __syncwarp();
+  }
+}
+
 // ---- balanced closed-system mode -----------------------------------------------------------------------------------------
 // Same three kernels as the chunk-parallel closed-system mode (K1 exponentials + running totals, K2u boundary operators,
 // K3u conjugation sweep with the trace-dots), but the (chain, slice) index space is cut into exactly as many contiguous,
