@@ -36,6 +36,7 @@ struct qoc_handle {
   // serial boundary stage of one range overlap with the bulk work of the others
   static constexpr int MAX_PARTS = 8;
   int parts = 1;
+  int part_lo[MAX_PARTS + 1] = {};       // chain range of every part (later parts smaller: their boundary + sweep stages are the tail)
   cudaStream_t aux[MAX_PARTS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_PARTS] = {};
   // balanced closed-system mode: the (chain, slice) space cut into one equal range per resident warp (BalTables)
@@ -170,7 +171,9 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     if (const char* e = getenv("QOC_HAVE_P")) h->have_P = atoi(e) != 0;   // tuning override
     if (h->chunked) {
       h->have_P = 0;
-      h->Cn = std::max(2, std::min((8192 + h->n_groups - 1) / h->n_groups, std::max(2, d.N / 16)));   // ~8192 warps measured best
+      // ~8192 warps measured best for the general kernels; the closed-system kernels (forked chain ranges) like >= 16 chunks
+      // at <= 1024 chains (1024 chains: 8 / 12 / 16 chunks 0.593 / 0.593 / 0.580 ms; 512 chains: 16 / 20 / 24 / 32 0.311 / 0.325 / 0.331 / 0.336)
+      h->Cn = std::max(2, std::min(std::max((8192 + h->n_groups - 1) / h->n_groups, d.gradient == QOC_GRAD_FIRST_ORDER ? 16 : 2), std::max(2, d.N / 16)));
       if (const char* e = getenv("QOC_CHUNKS")) h->Cn = std::max(2, std::min(atoi(e), d.N));
       h->Cn = std::min(h->Cn, d.N / 2);              // every chunk needs at least two slices
       if (h->Cn < 2) { h->chunked = 0; h->Cn = 1; }
@@ -229,6 +232,15 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
       h->parts = h->n_groups >= 64 ? 4 : 1;                        // measured on cfg4 shards (profiles/README.md)
       if (const char* e = getenv("QOC_PARTS")) h->parts = std::max(1, std::min(atoi(e), (int)qoc_handle::MAX_PARTS));
       h->parts = std::min(h->parts, std::max(1, h->n_groups / 4));
+      {
+        double skew = 1.0;                                           // part i gets a share proportional to skew^i
+        if (const char* e = getenv("QOC_PART_SKEW")) skew = std::max(0.1, std::min(atof(e), 1.0));
+        double tot = 0, acc = 0, wgt = 1.0;
+        for (int i = 0; i < h->parts; i++) { tot += wgt; wgt *= skew; }
+        wgt = 1.0;
+        for (int i = 0; i < h->parts; i++) { h->part_lo[i] = (int)std::lround(acc / tot * h->n_groups); acc += wgt; wgt *= skew; }
+        h->part_lo[h->parts] = h->n_groups;
+      }
       if (h->parts > 1) {
         CRC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         for (int i = 1; i < h->parts; i++) {
@@ -529,7 +541,7 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
     for (int i = 0; i < parts; i++) {                       // chains [w0, w1) on their own stream: expm -> boundary -> sweep
       cudaStream_t ps = i == 0 ? st : h->aux[i];
       if (i > 0) QOC_CUDA(h, cudaStreamWaitEvent(ps, h->ev_fork, 0));
-      const int w0 = (int)((long)i * h->n_groups / parts), w1 = (int)((long)(i + 1) * h->n_groups / parts);
+      const int w0 = h->part_lo[i], w1 = h->part_lo[i + 1];
       PhasedParams q = p;
       q.w_off = w0; q.w_cnt = w1 - w0;
       const unsigned gchunks = (unsigned)(((long)q.w_cnt * h->Cn + 3) / 4);

@@ -113,6 +113,13 @@ class GrapeEvaluator:
             return float(F[0]), (None if Gk is None else np.ascontiguousarray(Gk[0]))
         return F, Gk
 
+    def eval_raw(self, xb, F, G=None, allreduce=False):
+        """The bare C-ABI call on caller-owned buffers in the ABI's own layout (what a Julia `ccall` passes): xb [R][N][K]
+        float64 C-contiguous (= Julia's K x N column-major control_array per pulse), F [R], G [R][N][K] or None.  No
+        per-call allocation or transposition on the Python side."""
+        fn = self._lib.qoc_eval_allreduce if allreduce else self._lib.qoc_eval
+        self._check(fn(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
+
     def eval_device(self, x_dev_ptr, fg_dev_ptr, want_grad=True, stream=None):
         """Asynchronous evaluation on device pointers (ints): x [R][N][K], FG [R][1 + N*K]."""
         self._check(self._lib.qoc_eval_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
