@@ -48,24 +48,4 @@ phased_fn pick_sweep_unitary(int NB, int CPW) {
 
 phased_fn pick_sweep_unitary_dmma() { return sweep_unitary_dmma_kernel; }
 int sweep_unitary_dmma_smem() { return (1024 + 4 * 8 * DOT_LD) * (int)sizeof(double); }
-bal_fn pick_bal_expm(int NB, int CPW) {
-  if (NB == 2) return bal_expm_kernel<2, 1>;
-  if (CPW == 4) return bal_expm_kernel<1, 4>;
-  if (CPW == 2) return bal_expm_kernel<1, 2>;
-  return bal_expm_kernel<1, 1>;
-}
-bal_fn pick_bal_boundary(int NB, int CPW, int sys) {
-  const bool u = sys == SYS_UNITARY;
-  if (NB == 2) return u ? bal_boundary_kernel<2, 1, SYS_UNITARY> : bal_boundary_kernel<2, 1, SYS_DENSITY>;
-  if (CPW == 4) return u ? bal_boundary_kernel<1, 4, SYS_UNITARY> : bal_boundary_kernel<1, 4, SYS_DENSITY>;
-  if (CPW == 2) return u ? bal_boundary_kernel<1, 2, SYS_UNITARY> : bal_boundary_kernel<1, 2, SYS_DENSITY>;
-  return u ? bal_boundary_kernel<1, 1, SYS_UNITARY> : bal_boundary_kernel<1, 1, SYS_DENSITY>;
-}
-bal_fn pick_bal_sweep(int NB, int CPW) {
-  if (NB == 2) return bal_sweep_kernel<2, 1>;
-  if (CPW == 4) return bal_sweep_kernel<1, 4>;
-  if (CPW == 2) return bal_sweep_kernel<1, 2>;
-  return bal_sweep_kernel<1, 1>;
-}
-
 }  // namespace qoc

@@ -94,14 +94,6 @@ struct PhasedParams {
   double* gradc;
 };
 
-// balanced closed-system mode: host-built partition of the (chain, slice) index space (small_phased.cuh)
-struct BalTables {
-  const int* seg;        // [nseg + 1] flat (chain * N + slice) boundaries, ascending
-  const int* warp_seg;   // [nwarps + 1] first segment of every warp
-  const int* chain_seg;  // [n_groups + 1] first segment of every chain
-  int nwarps;
-};
-
 __host__ __device__ __forceinline__ int chunk_lo(int c, int N, int Cn) { return (int)((long)c * N / Cn); }
 
 // ---- kernel pickers (defined next to the kernels they instantiate) ---------------------------------------------------
@@ -118,10 +110,6 @@ phased_fn pick_boundary_unitary(int NB, int CPW, int sys);
 phased_fn pick_sweep_unitary(int NB, int CPW);
 phased_fn pick_sweep_unitary_dmma();     // D = 5..8 (NB = 1, one chain per warp), K <= 8: trace-dots on the tensor pipe
 int sweep_unitary_dmma_smem();           // its dynamic shared memory per CTA; grid = chains x ceil(Cn / 4)
-typedef void (*bal_fn)(const PhasedParams, const BalTables);
-bal_fn pick_bal_expm(int NB, int CPW);
-bal_fn pick_bal_boundary(int NB, int CPW, int sys);
-bal_fn pick_bal_sweep(int NB, int CPW);
 // ---- launch wrappers of the non-template kernels (defined in k_small_fused.cu); return cudaGetLastError() ---------------
 cudaError_t launch_pack(const PackParams& pp, long total, cudaStream_t st);
 cudaError_t launch_reduce_pass1(const double* gradc, const double* fomc, const double* wts, double* part, int M, int NK, int R,

@@ -39,10 +39,6 @@ struct qoc_handle {
   int part_lo[MAX_PARTS + 1] = {};       // chain range of every part (later parts smaller: their boundary + sweep stages are the tail)
   cudaStream_t aux[MAX_PARTS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_PARTS] = {};
-  // balanced closed-system mode: the (chain, slice) space cut into one equal range per resident warp (BalTables)
-  int bal = 0, bal_nwarps = 0, bal_nseg = 0;
-  int *bal_seg = nullptr, *bal_warp_seg = nullptr, *bal_chain_seg = nullptr;
-  double2 *bal_totT = nullptr, *bal_bW = nullptr;
   int unitary_fast = 1;                  // closed-system conjugation kernel when the problem is Hermitian (QOC_UNITARY_FAST=0 disables)
   double2 *bS = nullptr, *bC = nullptr;
   int NK = 0, red_chunk = 0, red_nchunks = 0;
@@ -184,50 +180,6 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
       h->chunked_closed = 1; h->Cn = std::min(8, std::max(2, d.N / 16));   // measured 2 / 3 / 4 / 6 / 8 chunks at 4096 chains: 2.452 / 2.421 / 2.408 / 2.400 / 2.398 ms
       if (const char* e = getenv("QOC_CHUNKS")) h->Cn = std::max(2, std::min(atoi(e), d.N / 2));   // tuning override
     }
-    // Closed systems with a first-order gradient (decided per system in qoc_set_system): balanced partition instead of a
-    // fixed chunk count.  One range per resident warp of the exponential kernel (5 CTAs of 4 warps per SM), ranges of at
-    // least 16 slices; QOC_BAL=0 falls back to the fixed-chunk kernels, QOC_BAL_WAVES scales the warp count (tuning).
-    if ((h->chunked || h->chunked_closed) && d.gradient == QOC_GRAD_FIRST_ORDER && (long)h->n_groups * d.N < (1L << 31)) {
-      h->bal = h->n_groups < 400;      // measured: static equal ranges win below ~400 chains, dynamic CTA scheduling of fixed chunks above
-      if (const char* e = getenv("QOC_BAL")) h->bal = atoi(e) != 0;
-    }
-    if (h->bal) {
-      int nsm = 148;
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, d.device);
-      double waves = 1.0;
-      if (const char* e = getenv("QOC_BAL_WAVES")) waves = std::max(0.05, atof(e));
-      const long total = (long)h->n_groups * d.N;
-      long nw = std::max(1L, std::min((long)(waves * nsm * 20), total / 16));
-      if (const char* e = getenv("QOC_BAL_WARPS")) nw = std::max(1L, std::min((long)atoi(e), total));
-      std::vector<int> seg, wseg, cseg(h->n_groups + 1, 0);
-      for (long i = 0; i < nw; i++) {
-        const long lo = i * total / nw, hi = (i + 1) * total / nw;
-        wseg.push_back((int)seg.size());
-        long b = lo;
-        while (b < hi) {                                           // split at chain boundaries
-          seg.push_back((int)b);
-          const long chain_end = (b / d.N + 1) * d.N;
-          b = std::min(hi, chain_end);
-        }
-      }
-      wseg.push_back((int)seg.size());
-      h->bal_nseg = (int)seg.size(); h->bal_nwarps = (int)nw;
-      seg.push_back((int)total);
-      {                                                            // first segment of every chain
-        int c = 0;
-        for (int sgi = 0; sgi < h->bal_nseg; sgi++) { const int w = seg[sgi] / d.N; while (c <= w) cseg[c++] = sgi; }
-        while (c <= h->n_groups) cseg[c++] = h->bal_nseg;
-      }
-      CR(dev_alloc(h, &h->bal_seg, seg.size()));
-      CR(dev_alloc(h, &h->bal_warp_seg, wseg.size()));
-      CR(dev_alloc(h, &h->bal_chain_seg, cseg.size()));
-      CRC(cudaMemcpy(h->bal_seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CRC(cudaMemcpy(h->bal_warp_seg, wseg.data(), wseg.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CRC(cudaMemcpy(h->bal_chain_seg, cseg.data(), cseg.size() * sizeof(int), cudaMemcpyHostToDevice));
-      const size_t E_ = (size_t)h->NB * h->NB * 64;
-      CR(dev_alloc(h, &h->bal_totT, (size_t)h->bal_nseg * E_));
-      CR(dev_alloc(h, &h->bal_bW, (size_t)h->bal_nseg * E_));
-    }
     if (h->chunked || h->chunked_closed) {
       h->parts = h->n_groups >= 64 ? 4 : 1;                        // measured on cfg4 shards (profiles/README.md)
       if (const char* e = getenv("QOC_PARTS")) h->parts = std::max(1, std::min(atoi(e), (int)qoc_handle::MAX_PARTS));
@@ -325,7 +277,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->comm_local) cudaFree(h->comm_local);
   if (h->comm_peers) cudaFree(h->comm_peers);
   if (h->comm_ctl) cudaFree(h->comm_ctl);
-  void* bufs[] = {h->bal_seg, h->bal_warp_seg, h->bal_chain_seg, h->bal_totT, h->bal_bW, h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
+  void* bufs[] = {h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hout) cudaFreeHost(h->hout);
@@ -518,7 +470,7 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
   int rc;
   PhasedParams p = phased_params(h, x_dev);
   const size_t E = (size_t)h->NB * h->NB * 64;
-  const size_t sys_bytes = (size_t)4 * (1 + h->d.K) * E * sizeof(double2);
+  const size_t sys_bytes = (size_t)(1 + h->d.K) * E * sizeof(double2);      // one copy per CTA (its 4 warps share a chain)
   p.sys_in_smem = sys_bytes + h->tb_bytes <= 96 * 1024;
   const int smem1 = h->tb_bytes + (p.sys_in_smem ? (int)sys_bytes : 0);
   typedef phased_fn kfn;
@@ -545,7 +497,7 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
       PhasedParams q = p;
       q.w_off = w0; q.w_cnt = w1 - w0;
       const unsigned gchunks = (unsigned)(((long)q.w_cnt * h->Cn + 3) / 4);
-      k1<<<gchunks, 128, smem1, ps>>>(q);
+      k1<<<(unsigned)((long)q.w_cnt * ((h->Cn + 3) / 4)), 128, smem1, ps>>>(q);
       if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
       kb<<<(unsigned)((q.w_cnt + 3) / 4), 128, h->tb_bytes, ps>>>(q);
       if ((rc = launch_check(h, "boundary_unitary_kernel")) != QOC_OK) return rc;
@@ -562,37 +514,12 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
     for (int i = 1; i < parts; i++) QOC_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
     return QOC_OK;
   }
-  k1<<<(unsigned)(((long)h->n_groups * h->Cn + 3) / 4), 128, smem1, st>>>(p);
+  k1<<<(unsigned)((long)h->n_groups * ((h->Cn + 3) / 4)), 128, smem1, st>>>(p);
   if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
   k2<<<(unsigned)((h->n_groups * 2 + 3) / 4), 128, 0, st>>>(p);
   if ((rc = launch_check(h, "boundary2_kernel")) != QOC_OK) return rc;
   cp.Cn = h->Cn; cp.bS = h->bS; cp.bC = h->bC; cp.tau_in = h->tau; cp.have_P = 1;
   return launch_chain(h, cp, sys, grad, st);
-}
-
-// balanced closed-system mode: exponentials + range totals, boundary operators per chain, conjugation sweep + trace-dots
-static int eval_balanced(qoc_handle* h, const double* x_dev, int sys, cudaStream_t st) {
-  int rc;
-  PhasedParams p = phased_params(h, x_dev);
-  p.totT = h->bal_totT; p.bS = h->bal_bW; p.store_plain = 1;
-  BalTables bt{h->bal_seg, h->bal_warp_seg, h->bal_chain_seg, h->bal_nwarps};
-  const size_t E = (size_t)h->NB * h->NB * 64;
-  const size_t sys_bytes = (size_t)4 * (1 + h->d.K) * E * sizeof(double2);
-  p.sys_in_smem = sys_bytes + h->tb_bytes <= 96 * 1024;
-  const int smem1 = h->tb_bytes + (p.sys_in_smem ? (int)sys_bytes : 0);
-  bal_fn k1 = pick_bal_expm(h->NB, h->CPW), kb = pick_bal_boundary(h->NB, h->CPW, sys), ks = pick_bal_sweep(h->NB, h->CPW);
-  if (smem1 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-  const unsigned grid = (unsigned)((h->bal_nwarps + 3) / 4);
-  k1<<<grid, 128, smem1, st>>>(p, bt);
-  if ((rc = launch_check(h, "bal_expm_kernel")) != QOC_OK) return rc;
-  kb<<<(unsigned)((h->n_groups + 3) / 4), 128, h->tb_bytes, st>>>(p, bt);
-  if ((rc = launch_check(h, "bal_boundary_kernel")) != QOC_OK) return rc;
-  const size_t bbytes = (size_t)4 * h->d.K * E * sizeof(double2);
-  p.sys_in_smem = bbytes <= 96 * 1024;
-  const int smem3 = p.sys_in_smem ? (int)bbytes : 0;
-  if (smem3 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-  ks<<<grid, 128, smem3, st>>>(p, bt);
-  return launch_check(h, "bal_sweep_kernel");
 }
 
 // rows_only: stop after the first reduction pass and leave the partial rows [R][red_nchunks][NK+1] in h->part (the
@@ -607,8 +534,6 @@ static int eval_small(qoc_handle* h, const double* x_dev, double* fg_dev, int wa
   if (!h->in_capture) QOC_CUDA(h, cudaEventRecord(h->ek0[slot], st));
   if (h->phased && want_grad) {
     if ((rc = eval_phased(h, x_dev, sys, grad, st)) != QOC_OK) return rc;
-  } else if (h->bal && h->herm && h->unitary_fast && grad == GRAD_FIRST) {
-    if ((rc = eval_balanced(h, x_dev, sys, st)) != QOC_OK) return rc;
   } else if ((h->chunked || (h->chunked_closed && h->herm && h->unitary_fast)) && want_grad) {
     if ((rc = eval_chunked(h, p, x_dev, sys, grad, st)) != QOC_OK) return rc;
   } else if (grad == GRAD_FIRST && h->herm && !h->have_P && h->unitary_fast) {

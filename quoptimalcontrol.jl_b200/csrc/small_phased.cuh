@@ -225,24 +225,27 @@ __global__ void __launch_bounds__(128) grad_slices_kernel(const PhasedParams p) 
 //     chunk total, T_new^T = T_old^T P_t^T = nt(Tt, P).
 template <int NB, int CPW, bool SH>
 __device__ __forceinline__ void chunk_expm_body(const PhasedParams& p, double2* smem) {
+  // grid: one CTA per (chain, group of 4 chunks) of the chains [w_off, w_off + w_cnt): its warps share the chain's system
+  // matrices, staged ONCE per CTA (was once per warp: 4x the L2 traffic and shared memory at every CTA start)
   const int warp_in_cta = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  if (gw >= p.w_cnt * p.Cn) return;                            // this launch covers the chains [w_off, w_off + w_cnt)
-  const int w = p.w_off + gw / p.Cn, c = gw % p.Cn;
+  const int Cg = (p.Cn + 3) >> 2;
+  const int wl = blockIdx.x / Cg, cg = blockIdx.x - wl * Cg;
+  const int w = p.w_off + wl, c = cg * 4 + warp_in_cta;
   const Lane L(threadIdx.x & 31);
   const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   constexpr int E = cm_elems<NB>();
   constexpr int TBW = NB * NB * 2 * TB_PLANE;
   const int N = p.N, K = p.K;
-  const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
   double* tb = reinterpret_cast<double*>(smem) + (size_t)warp_in_cta * TBW;
   const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
   if (SH) {
-    double2* mine = smem + (size_t)(blockDim.x >> 5) * TBW / 2 + (size_t)warp_in_cta * (1 + K) * E;
-    for (int i = L.lane; i < (1 + K) * E; i += 32) mine[i] = sysw[i];
-    __syncwarp();
-    sysw = mine;
+    double2* shared_sys = smem + (size_t)(blockDim.x >> 5) * TBW / 2;
+    for (int i = threadIdx.x; i < (1 + K) * E; i += blockDim.x) shared_sys[i] = sysw[i];
+    __syncthreads();
+    sysw = shared_sys;
   }
+  if (c >= p.Cn) return;
+  const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
   const double* xr = p.x + (size_t)sl.r * N * K;
   double2* stP = p.storePt + (size_t)w * N * E;
   double xpre[XPF];
@@ -464,144 +467,6 @@ __global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const Phased
     }
     __syncwarp();
   }
-}
-
-// ---- balanced closed-system mode -----------------------------------------------------------------------------------------
-// Same three kernels as the chunk-parallel closed-system mode (K1 exponentials + running totals, K2u boundary operators,
-// K3u conjugation sweep with the trace-dots), but the (chain, slice) index space is cut into exactly as many contiguous,
-// equally long ranges as there are resident warps (host-built tables, qocgrape.cu::build_balance): every warp gets the same
-// number of slices, the grid is one full wave for any chain count, and no warp idles in a ragged last wave.  A range that
-// crosses a chain boundary is split into segments; segment s covers flat indices [seg[s], seg[s+1]) of one chain.
-//   totT[s]  = product of the segment's propagators;   bS[s] = W at the segment's first slice.
-
-template <int NB, int CPW, bool SH>
-__device__ __forceinline__ void bal_expm_body(const PhasedParams& p, const BalTables& bt, double2* smem) {
-  const int warp_in_cta = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  if (gw >= bt.nwarps) return;
-  const Lane L(threadIdx.x & 31);
-  constexpr int E = cm_elems<NB>();
-  constexpr int TBW = NB * NB * 2 * TB_PLANE;
-  const int N = p.N, K = p.K;
-  double* tb = reinterpret_cast<double*>(smem) + (size_t)warp_in_cta * TBW;
-  double2* mine = smem + (size_t)(blockDim.x >> 5) * TBW / 2 + (size_t)warp_in_cta * (1 + K) * E;
-  int cur_sys = -1;
-  for (int s = bt.warp_seg[gw]; s < bt.warp_seg[gw + 1]; s++) {
-    const int b0 = bt.seg[s], b1 = bt.seg[s + 1];
-    const int w = b0 / N, t0 = b0 - w * N, t1 = b1 - w * N;
-    const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
-    const double2* sysw = p.sys + (size_t)sl.sysgroup * p.nmat * E;
-    if (SH) {
-      if (sl.sysgroup != cur_sys) {
-        __syncwarp();
-        for (int i = L.lane; i < (1 + K) * E; i += 32) mine[i] = sysw[i];
-        __syncwarp();
-        cur_sys = sl.sysgroup;
-      }
-      sysw = mine;
-    }
-    const double* xr = p.x + (size_t)sl.r * N * K;
-    double2* stP = p.storePt + (size_t)w * N * E;            // holds P (not P^T) in the closed-system modes
-    double xpre[XPF];
-#pragma unroll
-    for (int j = 0; j < XPF; j++) xpre[j] = (j < K) ? __ldg(xr + (size_t)t0 * K + j) : 0.0;
-    CM<NB> Tt;
-    for (int t = t0; t < t1; t++) {
-      const CM<NB> G = assemble_generator<NB, SH>(L, sysw, xr + (size_t)t * K, K, xpre);
-      if (t + 1 < t1) {
-#pragma unroll
-        for (int j = 0; j < XPF; j++) xpre[j] = (j < K) ? __ldg(xr + (size_t)(t + 1) * K + j) : 0.0;
-      }
-      const CM<NB> P = expm_t8<NB>(L, G, (float)p.theta, true, tb);
-      cm_store<NB>(L, stP + (size_t)t * E, P);
-      if (t == t0) Tt = transpose<NB>(L, P, tb);               // T^T of a one-slice range
-      else Tt = mul_nt<NB>(Tt, P);                             // T_new^T = T_old^T P_t^T
-    }
-    cm_store<NB>(L, p.totT + (size_t)s * E, transpose<NB>(L, Tt, tb));
-  }
-}
-template <int NB, int CPW>
-__global__ void __launch_bounds__(128, NB == 1 ? QOC_EXPM_MINB : 1) bal_expm_kernel(const PhasedParams p, const BalTables bt) {
-  extern __shared__ double2 smem[];
-  if (p.sys_in_smem) bal_expm_body<NB, CPW, true>(p, bt, smem); else bal_expm_body<NB, CPW, false>(p, bt, smem);
-}
-
-// K2u over the segments of one chain (any count >= 1): U_N^T, W_0, then W at the start of every further segment.
-template <int NB, int CPW, int SYS>
-__global__ void __launch_bounds__(128) bal_boundary_kernel(const PhasedParams p, const BalTables bt) {
-  extern __shared__ double2 smem[];
-  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= p.n_groups) return;
-  const Lane L(threadIdx.x & 31);
-  const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
-  constexpr int GS = 32 / CPW;
-  constexpr int E = cm_elems<NB>();
-  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
-  const int c0 = bt.chain_seg[w], Cn = bt.chain_seg[w + 1] - c0;
-  const double2* T = p.totT + (size_t)c0 * E;
-  CM<NB> Tn = cm_load<NB>(L, T + (size_t)(Cn > 1 ? 1 : 0) * E);               // loads run one segment ahead of the products
-  CM<NB> Ut = transpose<NB>(L, cm_load<NB>(L, T), tb);                        // U^T after segment 0
-  for (int c = 1; c < Cn; c++) {
-    const CM<NB> Tc = Tn;
-    if (c + 1 < Cn) Tn = cm_load<NB>(L, T + (size_t)(c + 1) * E);
-    Ut = mul_nt<NB>(Ut, Tc);                                                  // U^T T_c^T
-  }
-  double fom;
-  CM<NB> W = unitary_w0<NB, CPW, SYS>(L, Ut, cm_load<NB>(L, p.xi + (size_t)sl.sysgroup * E), cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E),
-                                     p.sign_static, 1.0 / ((double)p.D * (double)p.D), tb, fom);
-  if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
-  double2* bW = p.bS + (size_t)c0 * E;
-  cm_store<NB>(L, bW, W);
-  Tn = cm_load<NB>(L, T);
-  for (int c = 0; c + 1 < Cn; c++) {
-    const CM<NB> Tc = Tn;
-    if (c + 2 < Cn) Tn = cm_load<NB>(L, T + (size_t)(c + 1) * E);
-    const CM<NB> X = mul_nt<NB, true, false>(Tc, W);
-    W = mul_nt<NB>(Tc, X);
-    cm_store<NB>(L, bW + (size_t)(c + 1) * E, W);
-  }
-}
-
-template <int NB, int CPW, bool SH>
-__device__ __forceinline__ void bal_sweep_body(const PhasedParams& p, const BalTables& bt, double2* smem) {
-  const int warp_in_cta = threadIdx.x >> 5;
-  const int gw = blockIdx.x * (blockDim.x >> 5) + warp_in_cta;
-  if (gw >= bt.nwarps) return;
-  const Lane L(threadIdx.x & 31);
-  constexpr int E = cm_elems<NB>();
-  const int N = p.N, K = p.K;
-  double2* mine = smem + (size_t)warp_in_cta * K * E;
-  SmallParams sp; sp.M = p.M; sp.N = N; sp.K = K; sp.gradc = p.gradc;
-  int cur_sys = -1;
-  for (int s = bt.warp_seg[gw]; s < bt.warp_seg[gw + 1]; s++) {
-    const int b0 = bt.seg[s], b1 = bt.seg[s + 1];
-    const int w = b0 / N, t0 = b0 - w * N, t1 = b1 - w * N;
-    const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
-    const double2* Bmats = p.sys + (size_t)sl.sysgroup * p.nmat * E + E;
-    if (SH) {
-      if (sl.sysgroup != cur_sys) {
-        __syncwarp();
-        for (int i = L.lane; i < K * E; i += 32) mine[i] = Bmats[i];
-        __syncwarp();
-        cur_sys = sl.sysgroup;
-      }
-      Bmats = mine;
-    }
-    const double2* stP = p.storePt + (size_t)w * N * E;      // holds P (not P^T) in this mode
-    CM<NB> W = cm_load<NB>(L, p.bS + (size_t)s * E);
-    CM<NB> Pn = cm_load<NB>(L, stP + (size_t)t0 * E);
-    for (int t = t0; t < t1; t++) {
-      const CM<NB> P = Pn;
-      if (t + 1 < t1) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
-      emit_gradient<NB, CPW, SH, true>(sp, L, sl, Bmats, W, t);
-      if (t + 1 < t1) { const CM<NB> X = mul_nt<NB, true, false>(P, W); W = mul_nt<NB>(P, X); }
-    }
-  }
-}
-template <int NB, int CPW>
-__global__ void __launch_bounds__(128, NB == 1 ? QOC_SWEEP_MINB : 1) bal_sweep_kernel(const PhasedParams p, const BalTables bt) {
-  extern __shared__ double2 smem[];
-  if (p.sys_in_smem) bal_sweep_body<NB, CPW, true>(p, bt, smem); else bal_sweep_body<NB, CPW, false>(p, bt, smem);
 }
 
 }  // namespace qoc
