@@ -302,6 +302,81 @@ def secondary_config(name, R, qoc, torch, dev, local_rank, peak, threads, steps=
     return out
 
 
+def run_slice(args, cfg, rank, world, local_rank, dev, torch, dist, qoc):
+    """--mode slice: one large instance, slices block-partitioned over the ranks; the whole exchange + boundary-operator
+    stage runs inside the library over NVLink peer memory (qoc_eval_slice).  Strong scaling: total work fixed."""
+    A, B, Xi, Xt = cfg["members"][0]
+    K, N = cfg["x"].shape
+    D = A.shape[0]
+    if len(cfg["members"]) != 1 or D <= 16:
+        raise SystemExit("--mode slice needs a single large instance (cfg5)")
+    ev = qoc.NativeSliceParallelEvaluator(A, B, Xi, Xt, cfg["T"], N, cfg["sys_type"], dist=dist if world > 1 else None,
+                                          device=local_rank, gradient=cfg["gradient"])
+    lo, hi = ev.lo, ev.hi
+    xb = np.ascontiguousarray(cfg["x"][:, lo:hi].T)            # ABI layout [N_r][K]
+    F, G = np.empty(1), np.empty((hi - lo, K))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        ev.local._check(ev.local._lib.qoc_eval_slice(ev.local._h, xb.ctypes.data, F.ctypes.data, G.ctypes.data))
+    barrier()
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ev.local._check(ev.local._lib.qoc_eval_slice(ev.local._h, xb.ctypes.data, F.ctypes.data, G.ctypes.data))
+        dev_ms += ev.local.stats()["gpu_ms_last_eval"]
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    wall_ms, dev_ms = (t1 - t0) * 1e3 / args.steps, dev_ms / args.steps
+    launches = ev.local.stats()["launches_last_eval"]
+    if world > 1:
+        t = torch.tensor([wall_ms, dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_ms, dev_ms = float(t[0]), float(t[1])
+        blocks = [None] * world
+        dist.all_gather_object(blocks, np.ascontiguousarray(G.T))
+        Gfull = np.concatenate(blocks, axis=1)
+    else:
+        Gfull = np.ascontiguousarray(G.T)
+    if rank == 0:
+        parity = None
+        gpath = os.path.join(GOLDEN, "cfg5_full.npz")
+        if cfg["name"].startswith("cfg5") and os.path.exists(gpath):
+            z = np.load(gpath)
+            parity = parity_of(float(F[0]), Gfull, float(z["F"]), z["G"], "full size vs tests/golden/cfg5_full.npz, gradient blocks of all ranks")
+        peak, peak_src = fp64_peak()
+        credited, executed = products_per_slice(cfg, 2, K)
+        flops_rank = qoc.configs.alg_flops(cfg) / world
+        ratio = min(1.0, executed / credited) if executed else 1.0
+        ach = flops_rank / (dev_ms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": 1e3 / dev_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(cfg, 1),
+                "parallelism": f"slice-parallel x{world}: one instance, {N} slices block-partitioned, range propagators exchanged over NVLink peer "
+                               "memory, boundary operators on the library's own DMMA GEMM kernel (qoc_eval_slice)",
+                "e2e": {"value": 1e3 / wall_ms, "unit": UNIT, "h2d_bytes_per_step": int((hi - lo) * K * 8), "d2h_bytes_per_step": int(((hi - lo) * K + 1) * 8),
+                        "api": "qoc_eval_slice (host buffers)"},
+                "gpu_launches": int(launches) * args.steps, "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": ach * ratio, "peak": peak, "unit": "TFLOP/s", "frac": ach * ratio / peak,
+                             "achieved_credited": ach, "frac_credited": ach / peak, "products_per_slice": {"credited": credited, "executed": executed},
+                             "traffic": None, "kernel": "zgemm_dmma_kernel x %d launches per step per rank" % launches, "kernel_ms": dev_ms,
+                             "alg_flops_per_launch": flops_rank, "peak_source": peak_src},
+                "cpu_baseline": None, "parity": parity,
+                "timing_note": "`value`: CUDA events around the device part of qoc_eval_slice (max over ranks); `e2e`: wall clock of the same calls"}
+        print(json.dumps(line), file=_OUT, flush=True)
+    ev.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -314,6 +389,8 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (N = 1 default run only)")
     ap.add_argument("--single-process", action="store_true",
                     help="one process drives --gpus devices through ONE multi-device handle (qoc_desc.n_devices), no torchrun")
+    ap.add_argument("--mode", default="ensemble", choices=["ensemble", "slice"],
+                    help="slice: ONE instance (cfg5) with its time slices split over the ranks (qoc_eval_slice), strong scaling")
     ap.add_argument("--allreduce", default="oneshot", choices=["oneshot", "nccl"],
                     help="N > 1: fused one-shot all-reduce over NVLink peer memory (default) or torch.distributed NCCL")
     args = ap.parse_args()
@@ -342,6 +419,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.mode == "slice":
+        run_slice(args, cfg, rank, world, local_rank, dev, torch, dist, qoc)
+        return
     single_proc = args.single_process and world == 1 and args.gpus > 1
     n_gpus = args.gpus if single_proc else world
 

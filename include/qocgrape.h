@@ -59,6 +59,8 @@ extern "C" {
 #define QOC_SHARED_XT 8
 
 #define QOC_MAX_DEVICES 16
+#define QOC_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t): what the ranks exchange for the peer-memory entry points */
+#define QOC_MAX_RANKS 16
 
 typedef struct qoc_handle qoc_handle;
 
@@ -150,6 +152,20 @@ int qoc_propagators(qoc_handle* h, const double* x, double* out, int mode);
 int qoc_set_states(qoc_handle* h, const double* Xi, const double* Xt, int shared_flags);
 int qoc_eval_continue(qoc_handle* h, double* F, double* G);
 
+/* The same four steps inside the library, one process per GPU, no host staging and no library GEMMs: the range propagators
+ * are exchanged through CUDA-IPC peer buffers (flag signalling as in the all-reduce below) and the boundary operators are
+ * formed by the library's own DMMA GEMM kernel reading the peers' propagators straight over NVLink.
+ *   qoc_slice_export   allocate this rank's exchange buffer, return its IPC handle (handle for the range: D > 16, M = R = 1,
+ *                      QOC_FLAG_NO_PURE_STATE; its qoc_set_system Xi / Xt are placeholders)
+ *   qoc_slice_connect  open the peers' buffers (handles [world][QOC_IPC_HANDLE_BYTES]); Xi, Xt: the GLOBAL initial / target
+ *                      operators [D*D] of the whole problem (src/problems.jl:19-28)
+ *   qoc_eval_slice     x [N_r*K] = this rank's slices of the pulse; F = the full figure of merit (identical on every rank),
+ *                      G [N_r*K] = the gradient entries of this rank's slices (or NULL).  Every rank must call it, in the
+ *                      same order.  qoc_set_penalty does not apply here (C4 couples adjacent ranges). */
+int qoc_slice_export(qoc_handle* h, unsigned char* handle /* [QOC_IPC_HANDLE_BYTES] */);
+int qoc_slice_connect(qoc_handle* h, int world, int rank, const unsigned char* handles, const double* Xi, const double* Xt);
+int qoc_eval_slice(qoc_handle* h, const double* x, double* F, double* G);
+
 /* ---- multi-GPU, one process per GPU: fused one-shot all-reduce of [F|G] over NVLink peer memory -------------------
  * Replaces the cross-shard part of the ensemble reduction `sum(gradient .* wts, dims = 1)` (src/solve.jl:171-191) when
  * the members are sharded over GPUs.  Each rank publishes its weighted partial in a CUDA-IPC shared exchange buffer,
@@ -164,8 +180,6 @@ int qoc_eval_continue(qoc_handle* h, double* F, double* G);
  * The member reduction's second pass is folded into the all-reduce kernel, which keeps its epoch counter in device memory
  * (so the whole sequence is graph-replayable).  All calls of a handle must be issued in the same order on every rank;
  * qoc_comm_connect may be called once per handle. */
-#define QOC_IPC_HANDLE_BYTES 64
-#define QOC_MAX_RANKS 16
 int qoc_comm_export(qoc_handle* h, unsigned char* handle /* [QOC_IPC_HANDLE_BYTES] */);
 int qoc_comm_connect(qoc_handle* h, int world, int rank, const unsigned char* handles);
 int qoc_eval_allreduce_device(qoc_handle* h, const double* x_dev, double* FG_dev, int want_gradient, void* stream);

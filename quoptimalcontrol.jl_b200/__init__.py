@@ -5,7 +5,8 @@ in libqocgrape.so (hand-written CUDA, C ABI in include/qocgrape.h).  There is no
 from . import _lib, configs
 from ._lib import QocError
 from .build import build
-from .distributed import ShardedEnsembleEvaluator, SliceParallelEvaluator, shard_bounds
+from .distributed import (NativeSliceParallelEvaluator, ShardedEnsembleEvaluator, SliceParallelEvaluator,
+                          shard_bounds)
 from .evaluator import GrapeEvaluator
 from .problems import (ClosedStateTransfer, ClosedSystem, CoherenceTransfer, EnsembleProblem,
                        OpenSystem, OpenSystemCoherenceTransfer, Problem, StateTransfer, SystemType,

@@ -17,7 +17,8 @@ MAX_DEVICES = 16
 EXPORTS = ["qoc_version", "qoc_create", "qoc_destroy", "qoc_set_system", "qoc_eval", "qoc_eval_device",
            "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error",
            "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device", "qoc_minimize_lbfgs",
-           "qoc_set_states", "qoc_eval_continue", "qoc_eval_allreduce", "qoc_set_penalty"]
+           "qoc_set_states", "qoc_eval_continue", "qoc_eval_allreduce", "qoc_set_penalty",
+           "qoc_slice_export", "qoc_slice_connect", "qoc_eval_slice"]
 
 
 class QocDesc(C.Structure):
@@ -79,6 +80,9 @@ def load():
     lib.qoc_eval_allreduce_device.argtypes = [vp, vp, vp, C.c_int, vp]
     lib.qoc_eval_allreduce.argtypes = [vp, vp, vp, vp]
     lib.qoc_set_penalty.argtypes = [vp, C.c_double, C.c_double]
+    lib.qoc_slice_export.argtypes = [vp, vp]
+    lib.qoc_slice_connect.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    lib.qoc_eval_slice.argtypes = [vp, vp, vp, vp]
     lib.qoc_set_states.argtypes = [vp, vp, vp, C.c_int]
     lib.qoc_eval_continue.argtypes = [vp, vp, vp]
     for name in EXPORTS:

@@ -19,4 +19,11 @@ int big_eval(BigState* s, const double* x_dev, double* FG_dev, int want_grad, co
 int big_propagators(BigState* s, const double* x_dev, double2* out, int mode, cudaStream_t st, std::string& err, qoc_stats& stats);
 int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStream_t st, std::string& err, qoc_stats& stats);
 
+// slice-parallel evaluation of one instance over several GPUs (device-pointer entry points)
+int big_padded_dim(const BigState* s);
+int big_range_propagator_device(BigState* s, const double* x_dev, double2* U_out, cudaStream_t st, std::string& err, qoc_stats& stats);
+int big_set_states_device(BigState* s, const double2* Xi_pad, const double2* Xt_pad, cudaStream_t st, std::string& err);
+int big_matmul(BigState* s, int opA, int opB, const double2* A, const double2* B, double2* C, cudaStream_t st, std::string& err, qoc_stats& stats);
+int big_upload_states_padded(BigState* s, double2* dst, const double* src, std::string& err);
+
 }  // namespace qoc

@@ -922,4 +922,40 @@ int big_total_propagator(BigState* s, const double* x_dev, double2* out, cudaStr
   return QOC_OK;
 }
 
+// ---- device-pointer entry points for the slice-parallel evaluation (qocgrape.cu, qoc_eval_slice) ------------------------
+int big_padded_dim(const BigState* s) { return s->Dp; }
+
+// U (padded Dp x Dp) = product of the range's propagators for the pulse x_dev, left in `U_out` (may be an exchange buffer
+// that peers read); the propagators and chunk totals stay on the device for big_eval(..., reuse = true).  M = R = 1.
+int big_range_propagator_device(BigState* s, const double* x_dev, double2* U_out, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  if (s->d.M * s->d.R != 1 || s->pure.active) { err = "slice-parallel evaluation needs a dense-path handle with M = R = 1"; return QOC_EINVAL; }
+  int rc;
+  s->have_props = false;
+  if ((rc = big_set_batch(s, 0, 1, st, err))) return rc;
+  if ((rc = big_propagators_phase(s, 1, x_dev, st, err, stats))) return rc;
+  if ((rc = big_chunk_totals(s, 1, st, err, stats))) return rc;
+  const double2* Up; double2* spare;
+  if ((rc = big_scan(s, 1, 0, s->T, s->Q, s->tmpF, &Up, &spare, st, err, stats))) return rc;
+  BIG_CUDA(cudaMemcpyAsync(U_out, Up + (size_t)(s->Cn - 1) * s->DD, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  s->have_props = true;
+  return QOC_OK;
+}
+// install padded device matrices as the (single) member's Xi / Xt, asynchronously on st
+int big_set_states_device(BigState* s, const double2* Xi_pad, const double2* Xt_pad, cudaStream_t st, std::string& err) {
+  BIG_CUDA(cudaMemcpyAsync(s->Xi, Xi_pad, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(s->Xt, Xt_pad, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(s->XiQ, Xi_pad, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  BIG_CUDA(cudaMemcpyAsync(s->XtQ, Xt_pad, s->DD * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  return QOC_OK;
+}
+// C = op(A) op(B) for single padded Dp x Dp matrices (op: 0 = as is, 1 = conjugate transpose) on the DMMA GEMM kernel;
+// A and B may live in a peer GPU's memory (NVLink loads through cp.async)
+int big_matmul(BigState* s, int opA, int opB, const double2* A, const double2* B, double2* C, cudaStream_t st, std::string& err, qoc_stats& stats) {
+  GemmParams p{};
+  p.batch = 1; p.nout = 1;
+  p.A = bmat(A, 0); p.B = bmat(B, 0); p.out[0] = eout(bmat(C, 0));
+  return big_gemm(s, opA, opB, p, st, err, stats);
+}
+int big_upload_states_padded(BigState* s, double2* dst, const double* src, std::string& err) { return big_upload_padded(s, dst, src, 1, err); }
+
 }  // namespace qoc

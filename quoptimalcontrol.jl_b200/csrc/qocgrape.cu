@@ -69,6 +69,8 @@ struct qoc_handle {
   const double* ard_x[2] = {nullptr, nullptr};
   double* ard_fg[2] = {nullptr, nullptr};
   int ard_launches[2] = {0, 0};
+  // slice-parallel evaluation of one large instance (qoc_slice_*): exchange of the range propagators over peer memory
+  struct SliceComm* slice = nullptr;
   // control penalties C3 / C4 (qoc_set_penalty)
   double pen_amp = 0.0, pen_var = 0.0;
   // single-process multi-device parent (qoc_desc.n_devices > 1): the members are sharded over sub-handles
@@ -96,6 +98,7 @@ extern "C" const char* qoc_version(void) { return "qocgrape-b200 0.1 (sm_100a, D
 
 extern "C" const char* qoc_last_error(qoc_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static void slice_destroy(qoc_handle* h);
 static int multi_create(qoc_handle** out, const qoc_desc& d, int ndev);
 static void multi_destroy(qoc_handle* h);
 static int multi_set_system(qoc_handle* h, const double* A, const double* B, const double* Xi, const double* Xt, const double* wts, int shared_flags);
@@ -277,6 +280,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->comm_local) cudaFree(h->comm_local);
   if (h->comm_peers) cudaFree(h->comm_peers);
   if (h->comm_ctl) cudaFree(h->comm_ctl);
+  slice_destroy(h);
   void* bufs[] = {h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
@@ -1025,6 +1029,163 @@ extern "C" int qoc_eval_allreduce(qoc_handle* h, const double* x, double* F, dou
     QOC_CUDA(h, copy_result_async(h, grad));
     QOC_CUDA(h, cudaStreamSynchronize(h->stream));
   }
+  unpack_result(h, h->hout, F, G);
+  return QOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ slice-parallel evaluation
+// ONE large instance (D > 16, M = R = 1), its time slices block-partitioned over the ranks (SURVEY.md 8e "config 5", 8f
+// rank 4).  Each rank owns a handle for its range (N_r slices, duration T N_r / N).  Per evaluation, all on the handle's
+// stream and without host staging or library calls:
+//   1. range propagator U_r (exponentials, chunk totals, prefix products) written into this rank's exchange buffer,
+//   2. flag signal to every peer / wait for every peer's flag (peer-memory stores and local polls, as in the all-reduce),
+//   3. boundary operators with the repo's own DMMA GEMM kernel reading the peers' U_j straight over NVLink:
+//        L = U_{r-1} ... U_0,  R = U_{n-1} ... U_{r+1},
+//        S_lo = L Xi (L'),  C_hi = R' Xt (R)            (src/GRAPE.jl:226-228, :245-249 applied to whole ranges)
+//   4. the evaluation continues from the propagators of step 1 (no recomputation) with S_lo / C_hi as its Xi / Xt.
+// F is the full figure of merit on every rank (tr(S_t' C_t) does not depend on t), G the gradient entries of the rank's
+// slices.  Exchange buffer per rank: double2 U[2][Dp*Dp]; unsigned long long flags[2][QOC_MAX_RANKS]; epoch e uses half e & 1
+// (a rank can only be one epoch ahead of its slowest peer, see the all-reduce).
+struct SliceComm {
+  int world = 0, rank = -1;
+  unsigned long long epoch = 0;
+  size_t DDp = 0, flags_off = 0, bytes = 0;
+  char* local = nullptr;
+  char* peer_host[QOC_MAX_RANKS] = {};
+  char** peers = nullptr;                      // device copy of peer_host
+  double2 *Xi = nullptr, *Xt = nullptr;        // the GLOBAL initial / target operators, padded
+  double2 *L[2] = {nullptr, nullptr}, *R[2] = {nullptr, nullptr}, *tmp = nullptr, *Slo = nullptr, *Chi = nullptr;
+};
+
+__global__ void slice_signal_kernel(char* const* peers, int world, int rank, unsigned long long epoch, size_t flags_off) {
+  __threadfence_system();                      // U_r was written by the preceding kernels on this stream
+  if (threadIdx.x < world) {
+    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers[threadIdx.x] + flags_off) + (epoch & 1) * QOC_MAX_RANKS + rank;
+    *f = epoch;
+  }
+}
+__global__ void slice_wait_kernel(const char* mine, int world, unsigned long long epoch, size_t flags_off) {
+  const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(mine + flags_off) + (epoch & 1) * QOC_MAX_RANKS;
+  if (threadIdx.x < world) { while (f[threadIdx.x] < epoch) __nanosleep(64); }
+  __syncthreads();
+  __threadfence_system();
+}
+
+static void slice_destroy(qoc_handle* h) {
+  SliceComm* c = h->slice;
+  if (!c) return;
+  for (int r = 0; r < c->world; r++) if (r != c->rank && c->peer_host[r]) cudaIpcCloseMemHandle(c->peer_host[r]);
+  void* bufs[] = {c->local, c->peers, c->Xi, c->Xt, c->L[0], c->L[1], c->R[0], c->R[1], c->tmp, c->Slo, c->Chi};
+  for (void* b : bufs) if (b) cudaFree(b);
+  delete c;
+  h->slice = nullptr;
+}
+
+extern "C" int qoc_slice_export(qoc_handle* h, unsigned char* handle) {
+  if (!h || !handle) return QOC_EINVAL;
+  if (h->multi || h->path != 2 || h->d.M != 1 || h->d.R != 1) { h->err = "qoc_slice_export: needs a single-device handle with D > 16 and M = R = 1"; return QOC_EUNSUPPORTED; }
+  if (big_pure_active(h->big) ) { h->err = "qoc_slice_export: create the handle with QOC_FLAG_NO_PURE_STATE (dense path)"; return QOC_EUNSUPPORTED; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  if (!h->slice) {
+    SliceComm* c = new SliceComm();
+    h->slice = c;
+    const int Dp = big_padded_dim(h->big);
+    c->DDp = (size_t)Dp * Dp;
+    c->flags_off = 2 * c->DDp * sizeof(double2);
+    c->bytes = c->flags_off + 2 * QOC_MAX_RANKS * sizeof(unsigned long long);
+    QOC_CUDA(h, cudaMalloc((void**)&c->local, c->bytes));
+    QOC_CUDA(h, cudaMemset(c->local, 0, c->bytes));
+    for (double2** b : {&c->Xi, &c->Xt, &c->L[0], &c->L[1], &c->R[0], &c->R[1], &c->tmp, &c->Slo, &c->Chi}) QOC_CUDA(h, cudaMalloc((void**)b, c->DDp * sizeof(double2)));
+    QOC_CUDA(h, cudaDeviceSynchronize());
+    h->ws_bytes += (long long)(c->bytes + 9 * c->DDp * sizeof(double2));
+  }
+  cudaIpcMemHandle_t ih;
+  QOC_CUDA(h, cudaIpcGetMemHandle(&ih, h->slice->local));
+  memcpy(handle, &ih, QOC_IPC_HANDLE_BYTES);
+  return QOC_OK;
+}
+
+extern "C" int qoc_slice_connect(qoc_handle* h, int world, int rank, const unsigned char* handles, const double* Xi, const double* Xt) {
+  if (!h || !handles || !Xi || !Xt || world < 1 || world > QOC_MAX_RANKS || rank < 0 || rank >= world) { if (h) h->err = "qoc_slice_connect: bad argument"; return QOC_EINVAL; }
+  SliceComm* c = h->slice;
+  if (!c) { h->err = "qoc_slice_connect: call qoc_slice_export first"; return QOC_EINVAL; }
+  if (c->world > 0) { h->err = "qoc_slice_connect: this handle is already connected (once per handle)"; return QOC_EINVAL; }
+  QOC_CUDA(h, cudaSetDevice(h->d.device));
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { c->peer_host[r] = c->local; continue; }
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handles + (size_t)r * QOC_IPC_HANDLE_BYTES, QOC_IPC_HANDLE_BYTES);
+    void* ptr = nullptr;
+    QOC_CUDA(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_host[r] = (char*)ptr;
+  }
+  QOC_CUDA(h, cudaMalloc((void**)&c->peers, QOC_MAX_RANKS * sizeof(char*)));
+  QOC_CUDA(h, cudaMemcpy(c->peers, c->peer_host, QOC_MAX_RANKS * sizeof(char*), cudaMemcpyHostToDevice));
+  int rc;
+  if ((rc = big_upload_states_padded(h->big, c->Xi, Xi, h->err)) != QOC_OK) return rc;
+  if ((rc = big_upload_states_padded(h->big, c->Xt, Xt, h->err)) != QOC_OK) return rc;
+  c->world = world; c->rank = rank;
+  return QOC_OK;
+}
+
+extern "C" int qoc_eval_slice(qoc_handle* h, const double* x, double* F, double* G) {
+  if (!h) return QOC_EINVAL;
+  if (!x) { h->err = "qoc_eval_slice: null pulse"; return QOC_EINVAL; }
+  SliceComm* c = h->slice;
+  if (!c || c->world < 1) { h->err = "qoc_eval_slice: qoc_slice_connect has not been called"; return QOC_EINVAL; }
+  if (!h->system_set) { h->err = "qoc_eval_slice: qoc_set_system has not been called"; return QOC_EINVAL; }
+  const qoc_desc& d = h->d;
+  QOC_CUDA(h, cudaSetDevice(d.device));
+  cudaStream_t st = h->stream;
+  int rc;
+  h->st.launches_last_eval = 0;
+  h->st.n_evals++;
+  if ((rc = upload_x(h, x)) != QOC_OK) return rc;
+  QOC_CUDA(h, cudaEventRecord(h->ev0, st));
+  const unsigned long long epoch = ++c->epoch;
+  const bool unitary = d.sys_type == QOC_UNITARY_GATE;
+  auto U_of = [&](int r) { return reinterpret_cast<const double2*>(c->peer_host[r]) + (size_t)(epoch & 1) * c->DDp; };
+  // 1. range propagator into this rank's half of the exchange buffer
+  if ((rc = big_range_propagator_device(h->big, h->x, const_cast<double2*>(U_of(c->rank)), st, h->err, h->st)) != QOC_OK) return rc;
+  // 2. signal / wait
+  slice_signal_kernel<<<1, 32, 0, st>>>(c->peers, c->world, c->rank, epoch, c->flags_off);
+  if ((rc = launch_check(h, "slice_signal_kernel")) != QOC_OK) return rc;
+  slice_wait_kernel<<<1, 32, 0, st>>>(c->local, c->world, epoch, c->flags_off);
+  if ((rc = launch_check(h, "slice_wait_kernel")) != QOC_OK) return rc;
+  // 3. boundary operators (GEMM operands in peer memory are read over NVLink by the GEMM kernel itself)
+  auto mm = [&](int opA, int opB, const double2* A, const double2* B, double2* C) { return big_matmul(h->big, opA, opB, A, B, C, st, h->err, h->st); };
+  const double2 *Lp = nullptr, *Rp = nullptr;
+  for (int j = 0; j < c->rank; j++) {                      // L = U_{rank-1} ... U_0
+    if (j == 0) { Lp = U_of(0); continue; }
+    double2* dst = c->L[j & 1];
+    if ((rc = mm(0, 0, U_of(j), Lp, dst)) != QOC_OK) return rc;
+    Lp = dst;
+  }
+  for (int j = c->rank + 1; j < c->world; j++) {           // R = U_{world-1} ... U_{rank+1}
+    if (j == c->rank + 1) { Rp = U_of(j); continue; }
+    double2* dst = c->R[j & 1];
+    if ((rc = mm(0, 0, U_of(j), Rp, dst)) != QOC_OK) return rc;
+    Rp = dst;
+  }
+  const double2 *Slo = c->Xi, *Chi = c->Xt;
+  if (Lp) {
+    if (unitary) { if ((rc = mm(0, 0, Lp, c->Xi, c->Slo)) != QOC_OK) return rc; }
+    else { if ((rc = mm(0, 1, c->Xi, Lp, c->tmp)) != QOC_OK) return rc; if ((rc = mm(0, 0, Lp, c->tmp, c->Slo)) != QOC_OK) return rc; }
+    Slo = c->Slo;
+  }
+  if (Rp) {
+    if (unitary) { if ((rc = mm(1, 0, Rp, c->Xt, c->Chi)) != QOC_OK) return rc; }
+    else { if ((rc = mm(0, 0, c->Xt, Rp, c->tmp)) != QOC_OK) return rc; if ((rc = mm(1, 0, Rp, c->tmp, c->Chi)) != QOC_OK) return rc; }
+    Chi = c->Chi;
+  }
+  if ((rc = big_set_states_device(h->big, Slo, Chi, st, h->err)) != QOC_OK) return rc;
+  // 4. continue from the propagators of step 1
+  if (!G) QOC_CUDA(h, cudaMemsetAsync(h->out, 0, (size_t)(h->NK + 1) * sizeof(double), st));
+  if ((rc = big_eval(h->big, h->x, h->out, G != nullptr, h->wts, st, h->err, h->st, true)) != QOC_OK) return rc;
+  QOC_CUDA(h, cudaEventRecord(h->ev1, st));
+  QOC_CUDA(h, copy_result_async(h, G != nullptr));
+  QOC_CUDA(h, cudaStreamSynchronize(st));
+  QOC_CUDA(h, cudaEventElapsedTime(&h->st.gpu_ms_last_eval, h->ev0, h->ev1));
   unpack_result(h, h->hout, F, G);
   return QOC_OK;
 }

@@ -126,3 +126,48 @@ class SliceParallelEvaluator:
         F, G_r = self.local.eval_continue()
         blocks = self._all_gather(np.ascontiguousarray(G_r, dtype=np.float64).reshape(K, self.hi - self.lo))
         return F, np.concatenate(blocks, axis=1)
+
+
+class NativeSliceParallelEvaluator:
+    """Slice-parallel evaluation of one problem with everything after the pulse upload inside the library
+    (qoc_slice_export / qoc_slice_connect / qoc_eval_slice): one process per GPU, the range propagators are exchanged
+    through CUDA-IPC peer buffers and the boundary operators are formed by the library's own GEMM kernel reading the peers'
+    propagators over NVLink.  `dist` (any torch.distributed backend) only carries the 64-byte IPC handles once.
+
+    eval(x) takes the FULL pulse x[K, N] (every rank passes the same) and returns (F, G_local[K, N_r]); gather() assembles
+    the full gradient on every rank (for callers that want it everywhere; the optimiser only needs it on one)."""
+
+    def __init__(self, A, B, Xi, Xt, T, n_slices, sys_type, dist=None, device=0, gradient="first_order", convention="inplace"):
+        from .evaluator import GrapeEvaluator
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.N = int(n_slices)
+        if self.N < self.world:
+            raise ValueError("NativeSliceParallelEvaluator needs at least one slice per rank")
+        self.bounds = [shard_bounds(self.N, r, self.world) for r in range(self.world)]
+        self.lo, self.hi = self.bounds[self.rank]
+        D = np.asarray(A).shape[0]
+        I = np.eye(D, dtype=np.complex128)
+        self.local = GrapeEvaluator([(A, B, I, I)], float(T) * (self.hi - self.lo) / self.N, self.hi - self.lo, sys_type,
+                                    gradient=gradient, convention=convention, device=device, pure_state=False)
+        mine = self.local.slice_export()
+        handles = [mine]
+        if dist is not None and self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine)
+        self.local.slice_connect(self.world, self.rank, handles, Xi, Xt)
+
+    def eval(self, x, want_grad=True):
+        x = np.asarray(x, dtype=np.float64)
+        return self.local.eval_slice(np.ascontiguousarray(x[:, self.lo:self.hi]), want_grad)
+
+    def gather(self, G_local):
+        if self.dist is None or self.world == 1:
+            return G_local
+        blocks = [None] * self.world
+        self.dist.all_gather_object(blocks, G_local)
+        return np.concatenate(blocks, axis=1)
+
+    def close(self):
+        self.local.close()

@@ -142,6 +142,28 @@ class GrapeEvaluator:
         """qoc_eval_device + fused one-shot all-reduce: FG receives the sum over all ranks (async on `stream`)."""
         self._check(self._lib.qoc_eval_allreduce_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
 
+    # ---- slice-parallel evaluation of one large instance (one process per GPU, qoc_slice_*) ----
+    def slice_export(self) -> bytes:
+        buf = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        self._check(self._lib.qoc_slice_export(self._h, buf))
+        return buf.raw
+
+    def slice_connect(self, world, rank, handles, Xi, Xt):
+        """handles: `world` IPC handles in rank order; Xi, Xt: the GLOBAL initial / target operators of the problem."""
+        blob = b"".join(handles)
+        if len(blob) != world * _lib.IPC_HANDLE_BYTES:
+            raise ValueError("expected one 64-byte handle per rank")
+        xi, xt = _colmajor([Xi], self.D), _colmajor([Xt], self.D)
+        self._check(self._lib.qoc_slice_connect(self._h, int(world), int(rank), blob, xi.ctypes.data, xt.ctypes.data))
+
+    def eval_slice(self, x_local, want_grad=True):
+        """x_local[K, N_r]: this rank's slices.  Returns (F of the whole problem, G[K, N_r] of this rank's slices)."""
+        xb = self._pack_x(x_local)
+        F = np.empty(1)
+        G = np.empty((self.N, self.K)) if want_grad else None
+        self._check(self._lib.qoc_eval_slice(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
+        return float(F[0]), (None if G is None else np.ascontiguousarray(G.T))
+
     def minimize_lbfgs(self, x0, max_iters=0, history=0, g_tol=0.0, f_tol=-1.0, max_linesearch=0):
         """L-BFGS inside the library (qoc_minimize_lbfgs): returns (x[K, N], result dict).  Single pulse only."""
         xb = self._pack_x(x0)

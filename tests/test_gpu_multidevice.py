@@ -156,3 +156,23 @@ def test_penalty_gradient_is_the_derivative():
         e = np.zeros_like(x); e[c, t] = 1e-6
         fd = (_penalties(x + e, 0.3, 0.7)[0] - _penalties(x - e, 0.3, 0.7)[0]) / 2e-6
         assert abs(fd - G[c, t]) < 1e-8
+
+
+@pytest.mark.parametrize("sys_name", ["state", "unitary", "coherence"])
+@pytest.mark.parametrize("gradient", ["first_order", "exact"])
+def test_native_slice_parallel_one_rank(sys_name, gradient):
+    """world = 1: qoc_eval_slice (range propagator into the exchange buffer, flag round trip, continue with the global
+    states) must equal the plain evaluation."""
+    st = {"state": orc.STATE_TRANSFER, "unitary": orc.UNITARY_GATE, "coherence": orc.COHERENCE_TRANSFER}[sys_name]
+    D, K, N, T = 32, 2, 9, 0.8
+    A, B, Xi, Xt = random_system(D, K, seed=1000 + st, hermitian=(sys_name != "coherence"), unitary_targets=(sys_name == "unitary"))
+    x = np.random.default_rng(3).uniform(-1, 1, (K, N))
+    ev = qoc.NativeSliceParallelEvaluator(A, B, Xi, Xt, T, N, st, gradient=gradient)
+    for _ in range(3):                       # both halves of the exchange buffer
+        F, G = ev.eval(x)
+    ev.close()
+    if gradient == "exact":
+        Fo, Go = orc.exact_fom_and_gradient(A, B, x, T, Xi, Xt, st)
+    else:
+        Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, st)
+    assert_parity(F, G, Fo, Go)

@@ -113,3 +113,51 @@ def test_slice_parallel_two_gpus():
     for rank, errs in res:
         for name, ef, eg in errs:
             assert ef < 1e-10 and eg < 1e-8, (rank, name, ef, eg)
+
+
+def _native_slice_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import quoptimalcontrol_jl_b200 as qoc
+    from oracle import grape_oracle as orc
+    from conftest import random_system
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)   # carries the IPC handles
+    errs = []
+    for sys_type, name in [(orc.STATE_TRANSFER, "state"), (orc.UNITARY_GATE, "unitary"), (orc.COHERENCE_TRANSFER, "coherence")]:
+        D, K, N, T = 64, 2, 4 * world + 3, 0.9
+        A, B, Xi, Xt = random_system(D, K, seed=220 + sys_type, hermitian=(sys_type != orc.COHERENCE_TRANSFER),
+                                     unitary_targets=(sys_type == orc.UNITARY_GATE))
+        ev = qoc.NativeSliceParallelEvaluator(A, B, Xi, Xt, T, N, sys_type, dist=dist, device=rank)
+        for it in range(3):
+            x = np.random.default_rng(7 + it).uniform(-1, 1, (K, N))
+            F, G_loc = ev.eval(x)
+            G = ev.gather(G_loc)
+            Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, sys_type)
+            errs.append((name, abs(F - Fo) / max(1.0, abs(Fo)), float(np.max(np.abs(G - Go)) / max(np.max(np.abs(Go)), 1e-6))))
+        ev.close()
+    q.put((rank, errs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_native_slice_parallel(world):
+    """qoc_eval_slice over `world` GPUs: peer-memory exchange of the range propagators, boundary operators on the library's
+    own GEMM kernel over NVLink; same F and G as the single-device evaluation / the oracle, on every rank."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_native_slice_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        for name, ef, eg in errs:
+            assert ef < 1e-10 and eg < 1e-8, (rank, name, ef, eg)
