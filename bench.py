@@ -58,60 +58,68 @@ def config_dict(cfg, pulses_per_step):
             if store_gb > 0.5 else "no flush: working set %.3f GB, L2-resident between steps (stated, latency-bound case)" % store_gb}
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+print("ready", flush=True)
+while True:
+    print(time.time(), n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, n.nvmlDeviceGetPowerUsage(h) / 1000.0, int(fn(h)), flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML in a thread every ~2 ms
-    (nvidia-smi -lms as the fallback).  Started well before the timed loop so that short timed regions still get rows."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms by a helper
+    PROCESS (a polling thread in this process contends with the launch path of a host-driven multi-device step), with
+    nvidia-smi -lms as the fallback.  Started well before the timed loop so that short timed regions still get rows.
+    Timestamps are time.time() in both processes."""
     BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows, self.stop_flag, self.proc, self.nvml = [], False, None, None
+        self.rows, self.proc, self.source = [], None, None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nvml = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.maxclk = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.th = threading.Thread(target=self._poll, daemon=True)
-            self.th.start()
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() != "ready":
+                raise OSError("nvml helper failed")
+            self.source = "nvml"
         except Exception:
-            self.nvml = None
             try:
                 q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
                 self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(index), "-lms", "20"],
                                              stdout=subprocess.PIPE, text=True)
-                self.th = threading.Thread(target=self._read, daemon=True)
-                self.th.start()
+                self.source = "nvidia-smi"
             except OSError:
                 self.proc = None
-
-    def _poll(self):
-        n = self.nvml
-        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while not self.stop_flag:
-            try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
-                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                rs = int(reasons_fn(self.h))
-                self.rows.append((time.perf_counter(), sm, self.maxclk, pw, {v for k, v in self.BITS.items() if rs & k}))
-            except Exception:
-                pass
-            time.sleep(0.002)
+        if self.proc is not None:
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
 
     def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            f = [s.strip() for s in line.split(",")]
             try:
-                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]),
-                                  {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
+                if self.source == "nvml":
+                    f = line.split()
+                    rs = int(f[4])
+                    self.rows.append((float(f[0]), float(f[1]), float(f[2]), float(f[3]), {v for k, v in self.BITS.items() if rs & k}))
+                else:
+                    f = [x.strip() for x in line.split(",")]
+                    self.rows.append((time.time(), float(f[0]), float(f[1]), float(f[2]),
+                                      {n for n, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
             except (ValueError, IndexError):
                 continue
 
     def stop(self, t0, t1):
-        self.stop_flag = True
-        if self.proc is not None:
-            self.proc.terminate()
+        """t0, t1: time.time() stamps bracketing the timed region."""
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        self.th.join(timeout=1.0)
         inside = [r for r in self.rows if t0 <= r[0] <= t1]
         rows = inside or [r for r in self.rows if t0 - 0.25 <= r[0] <= t1 + 0.05]      # nearest rows under the same load
         if not rows:
@@ -119,7 +127,7 @@ class ClockSampler:
         reasons = set().union(*[r[4] for r in rows])
         return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
                 "power_w_max": float(max(r[3] for r in rows)), "samples": len(rows), "samples_in_timed_region": len(inside),
-                "source": "nvml" if self.nvml else "nvidia-smi", "reasons": sorted(reasons)}
+                "source": self.source, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------------------ oracle side
@@ -327,13 +335,13 @@ def run_slice(args, cfg, rank, world, local_rank, dev, torch, dist, qoc):
         ev.local._check(ev.local._lib.qoc_eval_slice(ev.local._h, xb.ctypes.data, F.ctypes.data, G.ctypes.data))
     barrier()
     dev_ms = 0.0
-    t0 = time.perf_counter()
+    t0, w0 = time.perf_counter(), time.time()
     for _ in range(args.steps):
         ev.local._check(ev.local._lib.qoc_eval_slice(ev.local._h, xb.ctypes.data, F.ctypes.data, G.ctypes.data))
         dev_ms += ev.local.stats()["gpu_ms_last_eval"]
     barrier()
-    t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if sampler else None
+    t1, w1 = time.perf_counter(), time.time()
+    clocks = sampler.stop(w0, w1) if sampler else None
     wall_ms, dev_ms = (t1 - t0) * 1e3 / args.steps, dev_ms / args.steps
     launches = ev.local.stats()["launches_last_eval"]
     if world > 1:
@@ -528,14 +536,14 @@ def main():
     barrier()
     ev.stats()                                    # reset the kernel-event ring
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start = time.perf_counter()
+    t_start, w_start = time.perf_counter(), time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     barrier()
-    t_end = time.perf_counter()
-    clocks = sampler.stop(t_start, t_end) if sampler else None
+    t_end, w_end = time.perf_counter(), time.time()
+    clocks = sampler.stop(w_start, w_end) if sampler else None
     ms = (t_end - t_start) * 1e3 / args.steps if single_proc else e0.elapsed_time(e1) / args.steps
     st = ev.stats()
     if world > 1:
