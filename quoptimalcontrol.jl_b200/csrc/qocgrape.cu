@@ -216,6 +216,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     size_t smem = (size_t)4 * h->nmat * E * sizeof(double2);
     h->sys_in_smem = smem + h->tb_bytes <= 96 * 1024;
     h->smem_bytes = h->tb_bytes + (h->sys_in_smem ? (int)smem : 0);
+
     CR(dev_alloc(h, &h->sys, (size_t)h->n_sysgroups * h->nmat * E));
     CR(dev_alloc(h, &h->xi, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->xt, (size_t)h->n_sysgroups * E));

@@ -81,28 +81,43 @@ template <int NB> __device__ __forceinline__ CM<NB> expm_t8(const Lane& L, CM<NB
 
 // Frechet derivative L_exp(G, Y) of the same scheme (derivative of each of the three products and of every
 // squaring).  Identity tr(W * L(G,E)) = tr(L(G,W) * E) lets ONE call per slice serve all K controls.
+// Ordered for short live ranges: the right factor R8 = x4 I + x5 G + x6 G2 + x7 G4 and its derivative are accumulated
+// term by term as soon as each (transposed) power exists, so G^T, Y^T, (G2)^T, (dG2)^T die after the second product instead
+// of surviving until the third (D = 16, 32 registers per matrix: local-memory stack 1008 -> 840 B in chain_kernel, 448 ->
+// 232 B in grad_slices_kernel).  Parking further matrices in shared memory explicitly brought that to 312 / 104 B but ran
+// 3 % slower (spills already hit L1 at shared-memory speed, and the operand prefetch had to go): not kept, profiles/README.md.
 template <int NB> __device__ __forceinline__ CM<NB> frechet_t8(const Lane& L, CM<NB> G, CM<NB> Y, float theta, bool herm, double* tb) {
   const int s = scaling_power(cm_norm1_bound<NB>(G), theta);
   if (s) { double sc = scalbn(1.0, -s); G = cm_scale<NB>(G, sc); Y = cm_scale<NB>(Y, sc); }
-  const CM<NB> Gt = herm ? cm_negconj<NB>(G) : transpose<NB>(L, G, tb);
-  const CM<NB> Yt = transpose<NB>(L, Y, tb);
-  const CM<NB> G2 = mul_nt<NB>(G, Gt);
-  CM<NB> dG2 = mul_nt<NB>(Y, Gt);
-  mul_nt_acc<NB>(G, Yt, dG2);                                     // Y G + G Y
-  const CM<NB> G2t = herm ? cm_conj<NB>(G2) : transpose<NB>(L, G2, tb);
-  const CM<NB> dG2t = transpose<NB>(L, dG2, tb);
-  CM<NB> Y1t = cm_scale<NB>(Gt, T8_X1); cm_axpy<NB>(Y1t, T8_X2, G2t);
-  CM<NB> dY1t = cm_scale<NB>(Yt, T8_X1); cm_axpy<NB>(dY1t, T8_X2, dG2t);
-  const CM<NB> G4 = mul_nt<NB>(G2, Y1t);
-  CM<NB> dG4 = mul_nt<NB>(dG2, Y1t);
-  mul_nt_acc<NB>(G2, dY1t, dG4);                                  // dG2 Y1 + G2 dY1
-  const CM<NB> G4t = transpose<NB>(L, G4, tb);
-  const CM<NB> dG4t = transpose<NB>(L, dG4, tb);
-  CM<NB> L8 = G4; cm_axpy<NB>(L8, T8_X3, G2);
-  CM<NB> dL8 = dG4; cm_axpy<NB>(dL8, T8_X3, dG2);
-  CM<NB> R8t = cm_scale<NB>(Gt, T8_X5); cm_axpy<NB>(R8t, T8_X6, G2t); cm_axpy<NB>(R8t, T8_X7, G4t);
-  cm_add_identity<NB>(L, R8t, T8_X4);
-  CM<NB> dR8t = cm_scale<NB>(Yt, T8_X5); cm_axpy<NB>(dR8t, T8_X6, dG2t); cm_axpy<NB>(dR8t, T8_X7, dG4t);
+  CM<NB> R8t, dR8t, Y1t, dY1t, G2, dG2;
+  {
+    const CM<NB> Gt = herm ? cm_negconj<NB>(G) : transpose<NB>(L, G, tb);
+    const CM<NB> Yt = transpose<NB>(L, Y, tb);
+    G2 = mul_nt<NB>(G, Gt);
+    dG2 = mul_nt<NB>(Y, Gt);
+    mul_nt_acc<NB>(G, Yt, dG2);                                   // Y G + G Y
+    R8t = cm_scale<NB>(Gt, T8_X5); cm_add_identity<NB>(L, R8t, T8_X4);
+    dR8t = cm_scale<NB>(Yt, T8_X5);
+    Y1t = cm_scale<NB>(Gt, T8_X1);
+    dY1t = cm_scale<NB>(Yt, T8_X1);
+  }
+  {
+    const CM<NB> G2t = herm ? cm_conj<NB>(G2) : transpose<NB>(L, G2, tb);
+    cm_axpy<NB>(Y1t, T8_X2, G2t); cm_axpy<NB>(R8t, T8_X6, G2t);
+    const CM<NB> dG2t = transpose<NB>(L, dG2, tb);
+    cm_axpy<NB>(dY1t, T8_X2, dG2t); cm_axpy<NB>(dR8t, T8_X6, dG2t);
+  }
+  CM<NB> L8 = mul_nt<NB>(G2, Y1t);                                // G4
+  CM<NB> dL8 = mul_nt<NB>(dG2, Y1t);
+  mul_nt_acc<NB>(G2, dY1t, dL8);                                  // dG4 = dG2 Y1 + G2 dY1
+  {
+    const CM<NB> G4t = transpose<NB>(L, L8, tb);
+    cm_axpy<NB>(R8t, T8_X7, G4t);
+    const CM<NB> dG4t = transpose<NB>(L, dL8, tb);
+    cm_axpy<NB>(dR8t, T8_X7, dG4t);
+  }
+  cm_axpy<NB>(L8, T8_X3, G2);                                     // L8 = G4 + x3 G2
+  cm_axpy<NB>(dL8, T8_X3, dG2);
   CM<NB> dP = Y; cm_axpy<NB>(dP, T8_Y2, dG2);
   mul_nt_acc<NB>(dL8, R8t, dP);
   mul_nt_acc<NB>(L8, dR8t, dP);                                   // dL8 R8 + L8 dR8 + Y + y2 dG2
