@@ -187,15 +187,20 @@ int qoc_eval_allreduce(qoc_handle* h, const double* x, double* F, double* G);
 
 /* ---- the caller of the path: L-BFGS inside the library ---------------------------------------
  * Replaces `Optim.optimize(Optim.only_fg!(topt), guess, LBFGS(), optim_options)` (src/solve.jl:138, :244) for a
- * single pulse (R = 1): two-loop recursion with `history` pairs and a backtracking Armijo line search on the host,
- * every evaluation being one qoc_eval (a CUDA-graph replay).  Stops on ||g||_inf <= g_tol (Optim's default criterion,
+ * single pulse (R = 1): two-loop recursion with `history` pairs (initial inverse Hessian scaled by s'y / y'y like Optim's
+ * scaleinvH0) and the Hager-Zhang line search with approximate Wolfe conditions (Optim.LBFGS's default, restated from the
+ * published algorithm with LineSearches.jl's default constants; initial trial step 1 = InitialStatic) on the host, every
+ * trial being one qoc_eval (a CUDA-graph replay; also on multi-device handles).  Stops on ||g||_inf <= g_tol (Optim's default criterion,
  * 1e-8), on a relative decrease below f_tol, or after max_iters iterations.  x0 / x_out: [N*K] like qoc_eval. */
+#define QOC_LS_HAGER_ZHANG 0
+#define QOC_LS_BACKTRACKING 1
 typedef struct qoc_lbfgs_options {
   int max_iters;        /* <= 0: 1000 (Optim.Options default) */
   int history;          /* <= 0: 10 (Optim.LBFGS default m) */
   double g_tol;         /* <= 0: 1e-8 */
   double f_tol;         /* < 0: 0 (disabled, Optim default) */
-  int max_linesearch;   /* <= 0: 30 */
+  int max_linesearch;   /* evaluations per line search; <= 0: 50 (Hager-Zhang, LineSearches' linesearchmax) / 30 (backtracking) */
+  int linesearch;       /* QOC_LS_HAGER_ZHANG (0, default: what Optim.LBFGS() uses) | QOC_LS_BACKTRACKING */
 } qoc_lbfgs_options;
 typedef struct qoc_lbfgs_result {
   double minimum;       /* res.minimum */

@@ -7,6 +7,7 @@ from ._lib import QocError
 from .build import build
 from .distributed import (NativeSliceParallelEvaluator, ShardedEnsembleEvaluator, SliceParallelEvaluator,
                           shard_bounds)
+from .dcrab import BatchedFidelity, dCRAB, nelder_mead_batched
 from .evaluator import GrapeEvaluator
 from .problems import (ClosedStateTransfer, ClosedSystem, CoherenceTransfer, EnsembleProblem,
                        OpenSystem, OpenSystemCoherenceTransfer, Problem, StateTransfer, SystemType,

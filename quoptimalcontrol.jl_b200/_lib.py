@@ -36,7 +36,7 @@ class QocStats(C.Structure):
 
 class QocLbfgsOptions(C.Structure):
     _fields_ = [("max_iters", C.c_int), ("history", C.c_int), ("g_tol", C.c_double), ("f_tol", C.c_double),
-                ("max_linesearch", C.c_int)]
+                ("max_linesearch", C.c_int), ("linesearch", C.c_int)]
 
 
 class QocLbfgsResult(C.Structure):

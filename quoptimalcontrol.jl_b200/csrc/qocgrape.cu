@@ -1429,7 +1429,8 @@ extern "C" int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbf
   const int m = opt && opt->history > 0 ? opt->history : 10;
   const double g_tol = opt && opt->g_tol > 0 ? opt->g_tol : 1e-8;
   const double f_tol = opt && opt->f_tol >= 0 ? opt->f_tol : 0.0;
-  const int max_ls = opt && opt->max_linesearch > 0 ? opt->max_linesearch : 30;
+  const bool use_hz = !(opt && opt->linesearch == QOC_LS_BACKTRACKING);
+  const int max_ls = opt && opt->max_linesearch > 0 ? opt->max_linesearch : (use_hz ? 50 : 30);
   std::vector<double> x(x0, x0 + n), g(n), xn(n), gn(n), dir(n), alpha(m), rho(m);
   std::vector<std::vector<double>> S(m, std::vector<double>(n)), Y(m, std::vector<double>(n));
   auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double s = 0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; };
@@ -1459,9 +1460,99 @@ extern "C" int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbf
     }
     double slope = dot(g, dir);
     if (!(slope < 0)) { for (int i = 0; i < n; i++) dir[i] = -g[i]; slope = -dot(g, g); stored = 0; }   // not a descent direction: restart
-    // backtracking Armijo line search (first iteration: scale the step to a unit-length move)
-    double step = (stored == 0) ? 1.0 / std::max(1.0, std::sqrt(dot(g, g))) : 1.0;
+    double step = 0.0;
     bool ok = false;
+    if (use_hz) {
+      // ---- Hager-Zhang line search (Hager & Zhang, SIAM J. Optim. 16 (2005), "Line Search Algorithm" with the approximate
+      // Wolfe conditions; the search Optim.LBFGS uses by default, src/solve.jl:138).  Constants are LineSearches.HagerZhang's
+      // defaults (delta 0.1, sigma 0.9, epsilon 1e-6, theta 0.5, gamma 0.66, rho 5); initial trial step 1 (InitialStatic).
+      // Every trial is one qoc_eval (value and gradient together); the accepted point is always the last one evaluated.
+      const double delta = 0.1, sigma = 0.9, theta = 0.5, gam = 0.66, rho_ = 5.0;
+      const double phi0 = f, dphi0 = slope, lim = phi0 + 1e-6 * std::fabs(phi0);
+      struct Pt { double a, f, d; };
+      int evals = 0, ls_rc = QOC_OK;
+      bool accepted = false;
+      auto phi = [&](double a) -> Pt {
+        for (int i = 0; i < n; i++) xn[i] = x[i] + a * dir[i];
+        int r = qoc_eval(h, xn.data(), &fnew, gn.data());
+        if (r != QOC_OK) ls_rc = r;
+        f_calls++; evals++;
+        Pt p{a, fnew, dot(gn, dir)};
+        if (!(std::isfinite(p.f) && std::isfinite(p.d))) { p.f = INFINITY; p.d = -1.0; }     // treated as "too far"
+        else if (a > 0 && ((delta * dphi0 >= (p.f - phi0) / a && p.d >= sigma * dphi0) ||
+                           ((2 * delta - 1) * dphi0 >= p.d && p.d >= sigma * dphi0 && p.f <= lim))) accepted = true;
+        return p;
+      };
+      auto live = [&]() { return !accepted && ls_rc == QOC_OK && evals < max_ls; };
+      auto u3 = [&](Pt a, Pt b, Pt& oa, Pt& ob) {          // shrink [a, b] with phi'(a) < 0, phi(b) > lim until phi'(d) >= 0
+        while (live()) {
+          Pt d = phi((1 - theta) * a.a + theta * b.a);
+          if (accepted) { oa = a; ob = d; return; }
+          if (d.d >= 0) { oa = a; ob = d; return; }
+          if (d.f <= lim) a = d; else b = d;
+        }
+        oa = a; ob = b;
+      };
+      auto update = [&](Pt a, Pt b, Pt c, Pt& oa, Pt& ob) {
+        if (!(c.a > a.a && c.a < b.a)) { oa = a; ob = b; return; }
+        if (c.d >= 0) { oa = a; ob = c; return; }
+        if (c.f <= lim) { oa = c; ob = b; return; }
+        u3(a, c, oa, ob);
+      };
+      auto secant = [](const Pt& a, const Pt& b) { return (a.a * b.d - b.a * a.d) / (b.d - a.d); };
+      Pt a{0.0, phi0, dphi0}, b{0.0, phi0, dphi0};
+      {  // bracket
+        Pt ci{0.0, phi0, dphi0};
+        double c = 1.0;
+        bool have = false;
+        while (live()) {
+          Pt cj = phi(c);
+          if (accepted) break;
+          if (cj.d >= 0) { a = ci; b = cj; have = true; break; }
+          if (cj.f > lim) { u3(Pt{0.0, phi0, dphi0}, cj, a, b); have = true; break; }
+          ci = cj; c *= rho_;
+        }
+        (void)have;
+      }
+      while (live()) {
+        const double width = b.a - a.a;
+        Pt A, B;
+        {  // secant^2
+          const double c = secant(a, b);
+          if (!std::isfinite(c)) break;
+          Pt pc = (c > a.a && c < b.a) ? phi(c) : Pt{c, 0, 0};
+          if (accepted) break;
+          update(a, b, pc, A, B);
+          if (!live()) break;
+          double cb = NAN;
+          if (pc.a == B.a && c > a.a && c < b.a) cb = secant(b, B);
+          else if (pc.a == A.a && c > a.a && c < b.a) cb = secant(a, A);
+          if (std::isfinite(cb) && cb > A.a && cb < B.a) {
+            Pt pcb = phi(cb);
+            if (accepted) break;
+            Pt A2, B2;
+            update(A, B, pcb, A2, B2);
+            A = A2; B = B2;
+          }
+        }
+        if (!live()) break;
+        if (B.a - A.a > gam * width) {
+          Pt pc = phi(0.5 * (A.a + B.a));
+          if (accepted) break;
+          Pt A2, B2;
+          update(A, B, pc, A2, B2);
+          A = A2; B = B2;
+        }
+        a = A; b = B;
+        if (!(b.a > a.a)) break;
+      }
+      if (ls_rc != QOC_OK) return ls_rc;
+      ok = accepted;
+      if (!ok && std::isfinite(fnew) && fnew < f) ok = true;     // budget exhausted: keep the last point if it still descends
+      if (ok) step = 1.0;                                       // xn, gn, fnew already hold the accepted point
+    } else {
+    // backtracking Armijo line search (first iteration: scale the step to a unit-length move)
+    step = (stored == 0) ? 1.0 / std::max(1.0, std::sqrt(dot(g, g))) : 1.0;
     for (int ls = 0; ls < max_ls; ls++) {
       for (int i = 0; i < n; i++) xn[i] = x[i] + step * dir[i];
       if ((rc = qoc_eval(h, xn.data(), &fnew, gn.data())) != QOC_OK) return rc;
@@ -1469,9 +1560,8 @@ extern "C" int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbf
       if (fnew <= f + 1e-4 * step * slope) { ok = true; break; }
       step *= 0.5;
     }
-    if (!ok) break;                                  // no acceptable step: stop at the current point
+    if (ok) {
     // expansion towards the (weak) Wolfe curvature condition: while the slope along dir is still steep, try doubling
-    {
       std::vector<double> xe(n), ge(n);
       for (int ex = 0; ex < 6 && dot(gn, dir) < 0.9 * slope; ex++) {
         const double s2 = 2.0 * step;
@@ -1483,6 +1573,8 @@ extern "C" int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbf
         step = s2; fnew = fe; xn.swap(xe); gn.swap(ge);
       }
     }
+    }
+    if (!ok) break;                                  // no acceptable step: stop at the current point
     for (int i = 0; i < n; i++) { S[head][i] = xn[i] - x[i]; Y[head][i] = gn[i] - g[i]; }
     const double sy = dot(S[head], Y[head]);
     const double fprev = f;

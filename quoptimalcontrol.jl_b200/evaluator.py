@@ -164,12 +164,13 @@ class GrapeEvaluator:
         self._check(self._lib.qoc_eval_slice(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
         return float(F[0]), (None if G is None else np.ascontiguousarray(G.T))
 
-    def minimize_lbfgs(self, x0, max_iters=0, history=0, g_tol=0.0, f_tol=-1.0, max_linesearch=0):
-        """L-BFGS inside the library (qoc_minimize_lbfgs): returns (x[K, N], result dict).  Single pulse only."""
+    def minimize_lbfgs(self, x0, max_iters=0, history=0, g_tol=0.0, f_tol=-1.0, max_linesearch=0, linesearch="hagerzhang"):
+        """L-BFGS inside the library (qoc_minimize_lbfgs): returns (x[K, N], result dict).  Single pulse only.
+        linesearch: "hagerzhang" (Optim.LBFGS's default) or "backtracking"."""
         xb = self._pack_x(x0)
         out = np.empty_like(xb)
         opt = _lib.QocLbfgsOptions(max_iters=int(max_iters), history=int(history), g_tol=float(g_tol), f_tol=float(f_tol),
-                                   max_linesearch=int(max_linesearch))
+                                   max_linesearch=int(max_linesearch), linesearch={"hagerzhang": 0, "backtracking": 1}[linesearch])
         res = _lib.QocLbfgsResult()
         self._check(self._lib.qoc_minimize_lbfgs(self._h, xb.ctypes.data, C.byref(opt), out.ctypes.data, C.byref(res)))
         return np.ascontiguousarray(np.swapaxes(out, 1, 2)[0]), {f: getattr(res, f) for f, _ in res._fields_}

@@ -90,7 +90,7 @@ def _optimize(ev, guess, options):
         return F, G.ravel()
 
     opts = {"maxiter": 1000, "gtol": 1e-8, "ftol": 1e-15}
-    opts.update(options or {})
+    opts.update({k: v for k, v in (options or {}).items() if k != "linesearch"})
     res = minimize(topt, np.asarray(guess, dtype=np.float64).ravel(), jac=True, method="L-BFGS-B", options=opts)
     return _OptimResult(res, shape)
 
@@ -114,7 +114,7 @@ def solve(prob, alg=None):
         if getattr(alg, "optimizer", "scipy") == "native":
             o = alg.optim_options or {}
             x, info = ev.minimize_lbfgs(guess, max_iters=o.get("maxiter", o.get("iterations", 0)), g_tol=o.get("gtol", o.get("g_tol", 0.0)),
-                                        f_tol=o.get("ftol", o.get("f_tol", -1.0)))
+                                        f_tol=o.get("ftol", o.get("f_tol", -1.0)), linesearch=o.get("linesearch", "hagerzhang"))
             res = _NativeResult(x, info)
         else:
             res = _optimize(ev, guess, alg.optim_options)

@@ -105,22 +105,24 @@ def test_closure_matches_oracle_during_optimisation():
     assert abs(sol.fidelity - Fo) < 1e-12
 
 
+@pytest.mark.parametrize("linesearch", ["hagerzhang", "backtracking"])
 @pytest.mark.parametrize("kind", ["state", "unitary_adgrape", "ensemble"])
-def test_native_lbfgs_solves_reference_scenarios(kind):
-    """qoc_minimize_lbfgs (the optimiser loop inside the library) on the reference's scenarios, same assertions."""
+def test_native_lbfgs_solves_reference_scenarios(kind, linesearch):
+    """qoc_minimize_lbfgs (the optimiser loop inside the library) on the reference's scenarios, same assertions, with the
+    Hager-Zhang line search (Optim.LBFGS's default) and with plain backtracking."""
     import time
     if kind == "state":
         prob = qoc.Problem(B=[Sx, Sy], A=Sz, Xi=rho_init, Xt=rho_fin, T=1.0, n_controls=2, guess=_guess(2, 10, 11), sys_type=qoc.StateTransfer())
-        alg = qoc.GPUGRAPE(n_slices=10, optimizer="native")
+        alg = qoc.GPUGRAPE(n_slices=10, optimizer="native", optim_options={"linesearch": linesearch})
         target = orc.C1(rho_fin, rho_fin)
     elif kind == "unitary_adgrape":
         prob = qoc.Problem(B=[Sx, Sy], A=Sz, Xi=U_init, Xt=U_fin, T=1.0, n_controls=2, guess=_guess(2, 25, 12), sys_type=qoc.UnitaryGate())
-        alg = qoc.GPUGRAPE(n_slices=25, gradient="exact", optimizer="native")
+        alg = qoc.GPUGRAPE(n_slices=25, gradient="exact", optimizer="native", optim_options={"linesearch": linesearch})
         target = orc.C1(U_fin, U_fin)
     else:
         p0 = qoc.Problem(B=[Sx, Sy], A=Sz, Xi=rho_init, Xt=rho_fin, T=5.0, n_controls=2, guess=_guess(2, 25, 13), sys_type=qoc.StateTransfer())
         prob = qoc.EnsembleProblem(prob=p0, n_ens=5, A_g=A_gens, B_g=B_gens, XiG=lambda k: rho_init, XtG=odd_switch, wts=np.ones(5) / 5)
-        alg = qoc.GPUGRAPE(n_slices=25, optimizer="native")
+        alg = qoc.GPUGRAPE(n_slices=25, optimizer="native", optim_options={"linesearch": linesearch})
         target = orc.C1(rho_fin, rho_fin)
     t0 = time.perf_counter(); sol = qoc.solve(prob, alg); t_native = time.perf_counter() - t0
     assert sol.result.minimum - target < tol * 10
@@ -129,5 +131,5 @@ def test_native_lbfgs_solves_reference_scenarios(kind):
     alg2 = qoc.GPUGRAPE(n_slices=alg.n_slices, gradient=alg.gradient, optimizer="scipy")
     t0 = time.perf_counter(); sol2 = qoc.solve(prob, alg2); t_scipy = time.perf_counter() - t0
     assert sol2.result.minimum - target < tol * 10
-    print(f"{kind}: native {sol.result.iterations} it / {sol.result.f_calls} evals in {t_native*1e3:.1f} ms (min {sol.result.minimum:.6f}); "
+    print(f"{kind} [{linesearch}]: native {sol.result.iterations} it / {sol.result.f_calls} evals in {t_native*1e3:.1f} ms (min {sol.result.minimum:.6f}); "
           f"scipy {sol2.result.iterations} it / {sol2.result.f_calls} evals in {t_scipy*1e3:.1f} ms (min {sol2.result.minimum:.6f})")
