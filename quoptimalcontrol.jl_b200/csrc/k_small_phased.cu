@@ -46,6 +46,8 @@ phased_fn pick_sweep_unitary(int NB, int CPW) {
   return sweep_unitary_kernel<1, 1>;
 }
 
+phased_fn pick_chunk_expm_dmma() { return chunk_expm_dmma_kernel; }
+int chunk_expm_dmma_smem() { return (1024 + 4 * ASM_WARP_DOUBLES) * (int)sizeof(double); }
 phased_fn pick_sweep_unitary_dmma() { return sweep_unitary_dmma_kernel; }
 int sweep_unitary_dmma_smem() { return (1024 + 4 * 8 * DOT_LD) * (int)sizeof(double); }
 }  // namespace qoc

@@ -108,6 +108,8 @@ phased_fn pick_chunk_expm(int NB, int CPW);
 phased_fn pick_boundary2(int NB, int CPW, int sys);
 phased_fn pick_boundary_unitary(int NB, int CPW, int sys);
 phased_fn pick_sweep_unitary(int NB, int CPW);
+phased_fn pick_chunk_expm_dmma();         // D = 5..8 (NB = 1, one chain per warp), K <= 7: generator assembly on the tensor pipe
+int chunk_expm_dmma_smem();
 phased_fn pick_sweep_unitary_dmma();     // D = 5..8 (NB = 1, one chain per warp), K <= 8: trace-dots on the tensor pipe
 int sweep_unitary_dmma_smem();           // its dynamic shared memory per CTA; grid = chains x ceil(Cn / 4)
 // ---- launch wrappers of the non-template kernels (defined in k_small_fused.cu); return cudaGetLastError() ---------------

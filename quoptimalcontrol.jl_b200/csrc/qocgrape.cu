@@ -483,6 +483,13 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
   if (smem1 > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
   const bool closed = grad == GRAD_FIRST && h->herm && h->unitary_fast;     // closed-system conjugation recursion
   p.store_plain = closed;
+  bool asm_on_dmma = h->NB == 1 && h->CPW == 1 && h->d.K <= 7;             // generator assembly as a batched DMMA product
+  if (const char* e = getenv("QOC_ASM_DMMA")) asm_on_dmma = asm_on_dmma && atoi(e) != 0;      // A/B testing
+  int smem1_used = smem1;
+  if (asm_on_dmma) {
+    k1 = pick_chunk_expm_dmma(); smem1_used = chunk_expm_dmma_smem();
+    if (smem1_used > 48 * 1024) QOC_CUDA(h, cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1_used));
+  }
   if (closed) {
     kfn kb = pick_boundary_unitary(h->NB, h->CPW, sys), ks = pick_sweep_unitary(h->NB, h->CPW);
     const size_t bbytes = (size_t)4 * h->d.K * E * sizeof(double2);
@@ -502,7 +509,7 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
       PhasedParams q = p;
       q.w_off = w0; q.w_cnt = w1 - w0;
       const unsigned gchunks = (unsigned)(((long)q.w_cnt * h->Cn + 3) / 4);
-      k1<<<(unsigned)((long)q.w_cnt * ((h->Cn + 3) / 4)), 128, smem1, ps>>>(q);
+      k1<<<(unsigned)((long)q.w_cnt * ((h->Cn + 3) / 4)), 128, smem1_used, ps>>>(q);
       if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
       kb<<<(unsigned)((q.w_cnt + 3) / 4), 128, h->tb_bytes, ps>>>(q);
       if ((rc = launch_check(h, "boundary_unitary_kernel")) != QOC_OK) return rc;
@@ -519,7 +526,7 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
     for (int i = 1; i < parts; i++) QOC_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
     return QOC_OK;
   }
-  k1<<<(unsigned)((long)h->n_groups * ((h->Cn + 3) / 4)), 128, smem1, st>>>(p);
+  k1<<<(unsigned)((long)h->n_groups * ((h->Cn + 3) / 4)), 128, smem1_used, st>>>(p);
   if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
   k2<<<(unsigned)((h->n_groups * 2 + 3) / 4), 128, 0, st>>>(p);
   if ((rc = launch_check(h, "boundary2_kernel")) != QOC_OK) return rc;

@@ -469,4 +469,84 @@ __global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const Phased
   }
 }
 
+// K1 with the generator assembly on the tensor pipe (D = 5..8, one chain per warp, K <= 7).
+// G_t = A~ + sum_j x[j,t] B~_j costs 24 dependent DFMA + 14 LDS.128 per slice in scalar form; like the trace-dots of the sweep
+// these scalar FP64 instructions queue behind the other warps' DMMAs.  Here the generators of 8 consecutive slices are
+// one batched product  Gflat[f][t] = sum_j' Coef[f][j'] * X[j'][t]  (m = flat matrix entry f, 16 blocks of 8; n = slice;
+// k = coefficient index j' = 0 (drift, X = 1), 1..K (controls)): 32 DMMA.8x8x4 per 8 slices, results staged in a per-warp
+// shared-memory tile from which every slice's G is read back in the register layout with two LDS.128.
+//   Ad [16 m-blocks][2 k-steps][32 lanes]   coefficient matrices in fragment order, shared by the CTA (same chain)
+//   per warp: [28 spare][8 rows x DOT_LD]   the transpose tile of warp_mat.cuh (160 doubles) aliases the spare doubles + row 0,
+//                                           which is dead as soon as slice 0 of the batch sits in registers
+constexpr int ASM_WARP_DOUBLES = 28 + 8 * DOT_LD;
+__global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  constexpr int NB = 1;
+  constexpr int E = cm_elems<NB>();
+  double* Ad = reinterpret_cast<double*>(smem);
+  const int warp = threadIdx.x >> 5;
+  double* tile = Ad + 1024 + warp * ASM_WARP_DOUBLES;      // transpose tile (2 * TB_PLANE doubles) ...
+  double* Gb = tile + 28;                                  // ... overlapping the first staging row
+  const int Cg = (p.Cn + 3) >> 2;
+  const int wl = blockIdx.x / Cg, cg = blockIdx.x - wl * Cg;
+  const int w = p.w_off + wl, c = cg * 4 + warp;
+  const Lane L(threadIdx.x & 31);
+  const Slot<1> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
+  const int N = p.N, K = p.K;
+  {
+    const double* sysd = reinterpret_cast<const double*>(p.sys + (size_t)sl.sysgroup * p.nmat * E);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+      const int ln = i & 31, ks = (i >> 5) & 1, mb = i >> 6, g = ln >> 2, q = ln & 3, j = 4 * ks + q;
+      Ad[i] = j <= K ? sysd[(size_t)j * (2 * E) + 8 * mb + g] : 0.0;
+    }
+  }
+  __syncthreads();
+  if (c >= p.Cn) return;
+  const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
+  const double* xr = p.x + (size_t)sl.r * N * K;
+  double2* stP = p.storePt + (size_t)w * N * E;
+  CM<NB> Tt;
+  for (int tb = t0; tb < t1; tb += 8) {
+    const int nb = min(8, t1 - tb);
+    {  // X fragments: lane (g = slice, q): k-step 0 -> (1, x_1, x_2, x_3)[q], k-step 1 -> x_{4+q}
+      const int ts = min(tb + L.g, t1 - 1);
+      const double* xs = xr + (size_t)ts * K;
+      const double b0 = L.q == 0 ? 1.0 : (L.q <= K ? __ldg(xs + L.q - 1) : 0.0);
+      const double b1 = 4 + L.q <= K ? __ldg(xs + 3 + L.q) : 0.0;
+      const double* ap = Ad + L.lane;
+      double* gp = Gb + (2 * L.q) * DOT_LD + L.g;
+#pragma unroll
+      for (int mb = 0; mb < 16; mb++) {
+        double d0 = 0.0, d1 = 0.0;
+        dmma(d0, d1, ap[(2 * mb) * 32], b0);
+        dmma(d0, d1, ap[(2 * mb + 1) * 32], b1);
+        gp[8 * mb] = d0; gp[8 * mb + DOT_LD] = d1;
+      }
+    }
+    __syncwarp();
+    for (int i = 0; i < nb; i++) {
+      const int t = tb + i;
+      CM<NB> G;
+      {
+        const double2 r = *reinterpret_cast<const double2*>(Gb + i * DOT_LD + 2 * L.lane);
+        const double2 m = *reinterpret_cast<const double2*>(Gb + i * DOT_LD + 64 + 2 * L.lane);
+        G.re[0][0][0] = r.x; G.re[0][0][1] = r.y; G.im[0][0][0] = m.x; G.im[0][0][1] = m.y;
+      }
+      __syncwarp();                                           // row 0 may now be overwritten by the transposes
+      const CM<NB> P = expm_t8<NB>(L, G, (float)p.theta, p.herm, tile);
+      if (p.store_plain) {
+        cm_store<NB>(L, stP + (size_t)t * E, P);
+        if (t == t0) Tt = transpose<NB>(L, P, tile); else Tt = mul_nt<NB>(Tt, P);
+      } else {
+        const CM<NB> Pt = transpose<NB>(L, P, tile);
+        cm_store<NB>(L, stP + (size_t)t * E, Pt);
+        Tt = (t == t0) ? Pt : mul_nt<NB>(Tt, P);
+      }
+    }
+    __syncwarp();
+  }
+  if (!p.store_plain) cm_store<NB>(L, p.totTt + ((size_t)w * p.Cn + c) * E, Tt);
+  cm_store<NB>(L, p.totT + ((size_t)w * p.Cn + c) * E, transpose<NB>(L, Tt, tile));
+}
+
 }  // namespace qoc
