@@ -1,5 +1,7 @@
+#!/bin/bash
+# Multi-GPU measurement set on one box: bash tools/run_multigpu.sh "8 4" r02x   (counts, tag)
+counts=${1:-"2"}; tag=${2:-r02}
 mkdir -p gpurun_out
-(timeout 500 python -m pytest tests/test_gpu_multigpu.py -q > gpurun_out/r02h_tests8.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02h_tests8.log); tail -4 gpurun_out/r02h_tests8.log
 summ() { python - "$1" <<'PY'
 import json,sys
 try:
@@ -9,9 +11,9 @@ try:
 except Exception as e: print(sys.argv[1], "FAILED", e)
 PY
 }
-for n in 8 4; do
-  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2961$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/r02h_scale_n$n.json 2> gpurun_out/r02h_scale_n$n.err; summ gpurun_out/r02h_scale_n$n.json
-  timeout 200 python bench.py --gpus $n --single-process --steps 20 --warmup 5 > gpurun_out/r02h_single_n$n.json 2> gpurun_out/r02h_single_n$n.err; summ gpurun_out/r02h_single_n$n.json
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2962$n bench.py --gpus $n --config cfg5 --mode slice --steps 5 --warmup 3 > gpurun_out/r02h_slice_n$n.json 2> gpurun_out/r02h_slice_n$n.err; summ gpurun_out/r02h_slice_n$n.json
+for n in $counts; do
+  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2961$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/${tag}_scale_n$n.json 2> gpurun_out/${tag}_scale_n$n.err; summ gpurun_out/${tag}_scale_n$n.json
+  timeout 200 python bench.py --gpus $n --single-process --steps 20 --warmup 5 > gpurun_out/${tag}_single_n$n.json 2> gpurun_out/${tag}_single_n$n.err; summ gpurun_out/${tag}_single_n$n.json
+  if [ -z "$NO_SLICE" ]; then timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2962$n bench.py --gpus $n --config cfg5 --mode slice --steps 5 --warmup 3 > gpurun_out/${tag}_slice_n$n.json 2> gpurun_out/${tag}_slice_n$n.err; summ gpurun_out/${tag}_slice_n$n.json; fi
 done
-timeout 100 python bench.py --steps 20 --warmup 5 --no-secondary > gpurun_out/r02h_scale_n1.json 2>/dev/null; summ gpurun_out/r02h_scale_n1.json
+timeout 100 python bench.py --steps 20 --warmup 5 --no-secondary > gpurun_out/${tag}_scale_n1.json 2>/dev/null; summ gpurun_out/${tag}_scale_n1.json
