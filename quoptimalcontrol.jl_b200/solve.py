@@ -29,6 +29,8 @@ class GPUGRAPE:
     optim_options: dict = field(default_factory=dict)
     optimizer: str = "scipy"           # "scipy" (L-BFGS-B, host) | "native" (qoc_minimize_lbfgs inside the library)
     pure_state: bool = True            # D > 16 pure-state transfers on sparse closed systems: state-vector sweep (same F, G)
+    devices: Any = None                # list of CUDA ordinals: ensemble members sharded over these GPUs inside this process
+    penalty: tuple = (0.0, 0.0)        # weights of the C3 / C4 control penalties (src/cost_functions.jl:29-39)
 
     @property
     def integrator(self):
@@ -110,7 +112,8 @@ def solve(prob, alg=None):
         tuples = [(prob.A, prob.B, prob.Xi, prob.Xt)]
         wts, guess = None, prob.guess
     with GrapeEvaluator(tuples, first.T, alg.n_slices, first.sys_type, wts=wts, gradient=alg.gradient,
-                        convention=alg.convention, device=alg.device, pure_state=getattr(alg, "pure_state", True)) as ev:
+                        convention=alg.convention, device=alg.device, pure_state=getattr(alg, "pure_state", True),
+                        devices=getattr(alg, "devices", None), penalty=getattr(alg, "penalty", (0.0, 0.0))) as ev:
         if getattr(alg, "optimizer", "scipy") == "native":
             o = alg.optim_options or {}
             x, info = ev.minimize_lbfgs(guess, max_iters=o.get("maxiter", o.get("iterations", 0)), g_tol=o.get("gtol", o.get("g_tol", 0.0)),

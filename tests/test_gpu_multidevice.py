@@ -176,3 +176,19 @@ def test_native_slice_parallel_one_rank(sys_name, gradient):
     else:
         Fo, Go = orc.fom_and_gradient_grape(A, B, x, T, Xi, Xt, st)
     assert_parity(F, G, Fo, Go)
+
+
+def test_solve_ensemble_on_a_multi_device_algorithm():
+    """solve(ens, GPUGRAPE(devices = [...])): the dispatch surface reaches the multi-device handle (mirror of
+    julia/GPUGRAPE.jl's `devices` keyword) and finds the same minimum as the single-device solve."""
+    Sx = np.array([[0, 1], [1, 0]], dtype=complex) / 2
+    Sy = np.array([[0, -1j], [1j, 0]], dtype=complex) / 2
+    Sz = np.diag([0.5, -0.5]).astype(complex)
+    rho0, rho1 = np.diag([1, 0]).astype(complex), np.diag([0, 1]).astype(complex)
+    guess = np.random.default_rng(4).random((2, 20))
+    p0 = qoc.Problem(B=[Sx, Sy], A=Sz, Xi=rho0, Xt=rho1, T=4.0, n_controls=2, guess=guess, sys_type=qoc.StateTransfer())
+    ens = qoc.EnsembleProblem(prob=p0, n_ens=5, A_g=lambda k: Sz * (1 + 0.02 * (k - 2)), B_g=lambda k: [Sx, Sy],
+                              XiG=lambda k: rho0, XtG=lambda k: rho1, wts=np.ones(5) / 5)
+    a = qoc.solve(ens, qoc.GPUGRAPE(n_slices=20, devices=_devices(3)))
+    b = qoc.solve(ens, qoc.GPUGRAPE(n_slices=20))
+    assert abs(a.fidelity - b.fidelity) < 1e-9 and a.fidelity < 0.7501
