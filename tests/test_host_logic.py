@@ -101,3 +101,21 @@ def test_slice_parallel_evaluator_single_process():
     import pytest
     with pytest.raises(ValueError):
         qoc.SliceParallelEvaluator(Xi, Xt, 1.0, 0, False, lambda n, dur: None)
+
+
+def test_bench_config_is_identical_in_both_arms():
+    """bench.py: the workload description must not differ between the GPU arm and --impl reference (driver's same_config)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    import quoptimalcontrol_jl_b200 as qoc
+    cfg = qoc.configs.config4(N=20, grid=2)
+    a, b = bench.config_dict(cfg, 1), bench.config_dict(cfg, 1)
+    assert a == b and set(a) == {"workload", "D", "K", "N", "M", "pulses_per_step", "gradient", "l2"}
+    assert a["D"] == 8 and a["K"] == 6 and a["M"] == 4 and "parallelism" not in a
+    p = bench.parity_of(1.0, np.ones((2, 3)), 1.0 + 1e-12, np.ones((2, 3)) * (1 + 1e-9), "x")
+    assert p["ok"] and p["grad_rel_err_inf"] < 1.1e-9
+    assert not bench.parity_of(1.0, np.ones((2, 3)), 1.0, np.ones((2, 3)) * 1.001, "x")["ok"]
