@@ -11,6 +11,12 @@
 #include <algorithm>
 #include <string>
 #include <vector>
+#include <thread>
+#include <atomic>
+#include <mutex>
+#include <condition_variable>
+#include <memory>
+#include <chrono>
 
 using namespace qoc;
 
@@ -61,6 +67,7 @@ struct qoc_handle {
   char* comm_peer_host[QOC_MAX_RANKS] = {};
   char** comm_peers = nullptr;           // device array of the peers' base pointers
   int comm_world = 0, comm_rank = -1;
+  bool comm_inproc = false;              // the peers' buffers are plain device pointers of the same process (threaded multi-device mode)
   unsigned long long* comm_ctl = nullptr;   // device: [0] epoch of the last finished all-reduce, [1] / [2] block tickets
   size_t comm_n = 0;
   cudaGraphExec_t ar_graph[2] = {nullptr, nullptr};      // qoc_eval_allreduce (host buffers): [0] value only, [1] + gradient
@@ -69,6 +76,8 @@ struct qoc_handle {
   const double* ard_x[2] = {nullptr, nullptr};
   double* ard_fg[2] = {nullptr, nullptr};
   int ard_launches[2] = {0, 0};
+  cudaGraphExec_t mt_graph[2] = {nullptr, nullptr};      // sub-handle of a threaded multi-device parent: H2D + kernels + all-reduce (+ D2H on the lead)
+  int mt_launches[2] = {0, 0};
   // slice-parallel evaluation of one large instance (qoc_slice_*): exchange of the range propagators over peer memory
   struct SliceComm* slice = nullptr;
   // control penalties C3 / C4 (qoc_set_penalty)
@@ -264,7 +273,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
 }
 
 static void drop_graphs(qoc_handle* h) {
-  for (cudaGraphExec_t* arr : {h->graph_exec, h->ar_graph, h->ard_graph})
+  for (cudaGraphExec_t* arr : {h->graph_exec, h->ar_graph, h->ard_graph, h->mt_graph})
     for (int i = 0; i < 2; i++) { if (arr[i]) cudaGraphExecDestroy(arr[i]); arr[i] = nullptr; }
   h->graph_launches[0] = h->graph_launches[1] = 0;
   h->ard_x[0] = h->ard_x[1] = nullptr;
@@ -277,7 +286,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->big) big_destroy(h->big);
   drop_graphs(h);
-  for (int r = 0; r < h->comm_world; r++) if (r != h->comm_rank && h->comm_peer_host[r]) cudaIpcCloseMemHandle(h->comm_peer_host[r]);
+  for (int r = 0; r < h->comm_world && !h->comm_inproc; r++) if (r != h->comm_rank && h->comm_peer_host[r]) cudaIpcCloseMemHandle(h->comm_peer_host[r]);
   if (h->comm_local) cudaFree(h->comm_local);
   if (h->comm_peers) cudaFree(h->comm_peers);
   if (h->comm_ctl) cudaFree(h->comm_ctl);
@@ -880,9 +889,16 @@ reduce_allreduce_kernel(const double* __restrict__ part, int nrows, int NK, int 
   }
   // (iii) wait for every rank's flag (own flag included) in OUR flag array
   const volatile unsigned long long* flg = reinterpret_cast<const volatile unsigned long long*>(peers[rank] + flags_off) + b * QOC_MAX_RANKS;
-  if (threadIdx.x < world) { while (flg[threadIdx.x] < epoch) __nanosleep(32); }
+  __shared__ int timed_out;
+  if (threadIdx.x == 0) timed_out = 0;
+  __syncthreads();
+  if (threadIdx.x < world) {                     // bounded: a peer that never arrives (failed launch) must not hang the GPU
+    const long long t0 = clock64();
+    while (flg[threadIdx.x] < epoch) { __nanosleep(32); if (clock64() - t0 > (1LL << 33)) { timed_out = 1; break; } }
+  }
   __syncthreads();
   __threadfence_system();
+  const double poison = timed_out ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;      // NaN result instead of a hang
   // (iv) sum over ranks in fixed order
   for (size_t gidx = blockIdx.x; gidx < ngroups; gidx += gridDim.x) {
     const size_t i = gidx * AR_ELEMS + el;
@@ -895,7 +911,7 @@ reduce_allreduce_kernel(const double* __restrict__ part, int nrows, int NK, int 
       double t = sm[0][el];
 #pragma unroll
       for (int l = 1; l < AR_LANES; l++) t += sm[l][el];
-      out[i] = t;
+      out[i] = t + poison;
     }
     __syncthreads();
   }
@@ -1215,6 +1231,17 @@ struct MultiState {
   const double** parts = nullptr;           // lead device: pointers to the shards' partial rows
   std::vector<double*> stage;               // lead-device copies of the partial rows when peer access is unavailable
   bool peer = true, use_graph = true;
+  // threaded mode (distinct devices with mutual peer access, D <= 16): one persistent launch thread per device replays that
+  // device's own graph (H2D, chain kernels, first reduction pass, fused fold + all-reduce over peer memory; D2H on the lead)
+  // -- the process-per-GPU data path inside one process, started by all threads at once instead of one 8-device graph
+  bool threaded = false, quit = false;
+  int cur_grad = 0;
+  std::vector<std::thread> workers;
+  std::atomic<int> gen{0};
+  std::unique_ptr<std::atomic<int>[]> done;
+  std::vector<int> rcs;
+  std::mutex mu;
+  std::condition_variable cv;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   int graph_launches[2] = {0, 0};
 };
@@ -1230,11 +1257,19 @@ __global__ void multi_sum_kernel(const double* const* __restrict__ parts, int n,
 static void multi_drop_graphs(qoc_handle* h) {
   if (!h->multi) return;
   for (auto& g : h->multi->graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+  for (qoc_handle* sh : h->multi->sub)
+    if (sh) for (auto& g : sh->mt_graph) { if (g) { cudaSetDevice(sh->d.device); cudaStreamSynchronize(sh->stream); cudaGraphExecDestroy(g); } g = nullptr; }
 }
 
 static void multi_destroy(qoc_handle* h) {
   MultiState* m = h->multi;
   if (!m) return;
+  if (!m->workers.empty()) {
+    { std::lock_guard<std::mutex> lk(m->mu); m->quit = true; }
+    m->cv.notify_all();
+    for (auto& t : m->workers) t.join();
+    m->workers.clear();
+  }
   if (!m->sub.empty() && m->sub[0]) { cudaSetDevice(m->dev[0]); cudaStreamSynchronize(m->sub[0]->stream); }
   multi_drop_graphs(h);
   for (qoc_handle* sh : m->sub) if (sh) qoc_destroy(sh);
@@ -1249,6 +1284,104 @@ static void multi_destroy(qoc_handle* h) {
   if (m->hout) cudaFreeHost(m->hout);
   delete m;
   h->multi = nullptr;
+}
+
+// ---- threaded mode -------------------------------------------------------------------------------------------------------
+// in-process communicator: every shard's exchange buffer is plain device memory that the other devices map by peer access
+static int multi_comm_setup(qoc_handle* h) {
+  MultiState* m = h->multi;
+  for (int r = 0; r < m->n; r++) {
+    qoc_handle* sh = m->sub[r];
+    QOC_CUDA(h, cudaSetDevice(m->dev[r]));
+    for (int j = 0; j < m->n; j++) {
+      if (j == r) continue;
+      cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[j], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e != cudaSuccess) { cudaGetLastError(); return QOC_EUNSUPPORTED; }
+    }
+    sh->comm_n = (size_t)h->d.R * (h->NK + 1);
+    const size_t bytes = 2 * sh->comm_n * sizeof(double) + 2 * QOC_MAX_RANKS * sizeof(unsigned long long);
+    QOC_CUDA(h, cudaMalloc((void**)&sh->comm_local, bytes));
+    QOC_CUDA(h, cudaMemset(sh->comm_local, 0, bytes));
+    QOC_CUDA(h, cudaMalloc((void**)&sh->comm_ctl, 4 * sizeof(unsigned long long)));
+    QOC_CUDA(h, cudaMemset(sh->comm_ctl, 0, 4 * sizeof(unsigned long long)));
+    QOC_CUDA(h, cudaDeviceSynchronize());
+  }
+  for (int r = 0; r < m->n; r++) {
+    qoc_handle* sh = m->sub[r];
+    QOC_CUDA(h, cudaSetDevice(m->dev[r]));
+    for (int j = 0; j < m->n; j++) sh->comm_peer_host[j] = m->sub[j]->comm_local;
+    QOC_CUDA(h, cudaMalloc((void**)&sh->comm_peers, QOC_MAX_RANKS * sizeof(char*)));
+    QOC_CUDA(h, cudaMemcpy(sh->comm_peers, sh->comm_peer_host, QOC_MAX_RANKS * sizeof(char*), cudaMemcpyHostToDevice));
+    sh->comm_world = m->n; sh->comm_rank = r; sh->comm_inproc = true;
+  }
+  return QOC_OK;
+}
+
+// one shard's share of an evaluation: replay (first: capture) its graph on its own stream; the lead also brings [F|G] home
+static int multi_shard_launch(qoc_handle* h, int r, bool grad) {
+  MultiState* m = h->multi;
+  qoc_handle* sh = m->sub[r];
+  const int gi = grad ? 1 : 0;
+  const size_t nx = (size_t)h->d.R * h->NK, rowlen = (size_t)h->d.R * (h->NK + 1), row = (size_t)h->NK + 1;
+  if (!sh->mt_graph[gi]) {
+    sh->pen_amp = h->pen_amp; sh->pen_var = h->pen_var;       // every shard applies them to its copy of the sum; the lead's is read
+    const bool ok = capture_graph(sh, &sh->mt_graph[gi], &sh->mt_launches[gi], [&]() {
+      bool k = cudaMemcpyAsync(sh->x, m->hx, nx * sizeof(double), cudaMemcpyHostToDevice, sh->stream) == cudaSuccess;
+      k = k && enqueue_allreduce(sh, sh->x, sh->out, grad, sh->stream) == QOC_OK;
+      if (r == 0 && k) {
+        if (grad) k = cudaMemcpyAsync(m->hout, sh->out, rowlen * sizeof(double), cudaMemcpyDeviceToHost, sh->stream) == cudaSuccess;
+        else k = cudaMemcpy2DAsync(m->hout, row * sizeof(double), sh->out, row * sizeof(double), sizeof(double), h->d.R, cudaMemcpyDeviceToHost, sh->stream) == cudaSuccess;
+      }
+      return k;
+    });
+    sh->st.n_evals--;
+    if (!ok) { sh->err = "multi-device: graph capture of a shard failed: " + sh->err; return QOC_ECUDA; }
+  }
+  if (cudaGraphLaunch(sh->mt_graph[gi], sh->stream) != cudaSuccess) { sh->err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(cudaGetLastError()); return QOC_ECUDA; }
+  sh->st.n_evals++; sh->st.n_launches += sh->mt_launches[gi]; sh->st.launches_last_eval = sh->mt_launches[gi];
+  return QOC_OK;
+}
+
+static void multi_worker(qoc_handle* h, int r) {
+  MultiState* m = h->multi;
+  cudaSetDevice(m->dev[r]);
+  int seen = 0;
+  for (;;) {
+    int g = m->gen.load(std::memory_order_acquire);
+    for (int spin = 0; g == seen && !m->quit && spin < 200000; spin++) g = m->gen.load(std::memory_order_acquire);   // ~100 us of spinning
+    if (g == seen && !m->quit) {
+      std::unique_lock<std::mutex> lk(m->mu);
+      m->cv.wait_for(lk, std::chrono::milliseconds(50), [&] { return m->quit || m->gen.load(std::memory_order_acquire) != seen; });
+      continue;
+    }
+    if (m->quit) return;
+    seen = g;
+    m->rcs[r] = multi_shard_launch(h, r, m->cur_grad != 0);
+    m->done[r].store(seen, std::memory_order_release);
+  }
+}
+
+static int multi_eval_threaded(qoc_handle* h, const double* x, double* F, double* G) {
+  MultiState* m = h->multi;
+  memcpy(m->hx, x, (size_t)h->d.R * h->NK * sizeof(double));
+  m->cur_grad = G != nullptr;
+  const int g = m->gen.load(std::memory_order_relaxed) + 1;
+  m->gen.store(g, std::memory_order_release);
+  m->cv.notify_all();
+  QOC_CUDA(h, cudaSetDevice(m->dev[0]));
+  int rc = multi_shard_launch(h, 0, G != nullptr);               // the calling thread drives the lead device itself
+  for (int r = 1; r < m->n; r++) {
+    while (m->done[r].load(std::memory_order_acquire) != g) std::this_thread::yield();
+    if (rc == QOC_OK && m->rcs[r] != QOC_OK) { rc = m->rcs[r]; h->err = "device " + std::to_string(m->dev[r]) + ": " + m->sub[r]->err; }
+  }
+  if (rc != QOC_OK) { if (h->err.empty()) h->err = m->sub[0]->err; cudaStreamSynchronize(m->sub[0]->stream); return rc; }
+  QOC_CUDA(h, cudaStreamSynchronize(m->sub[0]->stream));
+  long long launches = 0;
+  for (qoc_handle* sh : m->sub) launches += sh->st.launches_last_eval;
+  h->st.launches_last_eval = (int)launches; h->st.n_launches += launches; h->st.n_evals++;
+  unpack_result(h, m->hout, F, G);
+  return QOC_OK;
 }
 
 static int multi_create(qoc_handle** out, const qoc_desc& d, int ndev) {
@@ -1308,6 +1441,20 @@ static int multi_create(qoc_handle** out, const qoc_desc& d, int ndev) {
   if ((ce = cudaMemcpy((void*)m->parts, pp.data(), n * sizeof(double*), cudaMemcpyHostToDevice)) != cudaSuccess) return cfail(ce, "cudaMemcpy");
   if ((ce = cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return cfail(ce, "cudaEventCreate");
   h->path = m->sub[0]->path;
+  {  // threaded mode: distinct devices, warp-resident path, peer access both ways
+    bool distinct = true;
+    for (int a = 0; a < n; a++) for (int b = 0; b < a; b++) if (m->dev[a] == m->dev[b]) distinct = false;
+    bool want = distinct && m->use_graph && n <= QOC_MAX_RANKS;
+    if (const char* e = getenv("QOC_MULTI_THREADS")) want = want && atoi(e) != 0;      // A/B: fall back to the single multi-device graph
+    if (want && multi_comm_setup(h) == QOC_OK) {
+      m->threaded = true;
+      m->done.reset(new std::atomic<int>[n]);
+      for (int r = 0; r < n; r++) m->done[r].store(0);
+      m->rcs.assign(n, QOC_OK);
+      for (int r = 1; r < n; r++) m->workers.emplace_back(multi_worker, h, r);
+    }
+    cudaSetDevice(m->dev[0]);
+  }
   *out = h;
   return QOC_OK;
 }
@@ -1366,6 +1513,7 @@ static int multi_enqueue(qoc_handle* h, bool grad) {
 
 static int multi_eval(qoc_handle* h, const double* x, double* F, double* G) {
   MultiState* m = h->multi;
+  if (m->threaded) return multi_eval_threaded(h, x, F, G);
   const bool grad = G != nullptr;
   const int gi = grad ? 1 : 0;
   memcpy(m->hx, x, (size_t)h->d.R * h->NK * sizeof(double));

@@ -327,24 +327,32 @@ __global__ void __launch_bounds__(128) boundary2_kernel(const PhasedParams p) {
 // ---- chunk-parallel closed-system mode: K1 = chunk_expm (stores P, not P^T), K2u, K3u ---------------------------
 // K2u: one warp per group: U_N^T from the chunk totals, W_0 (unitary_w0), then the chunk-boundary operators
 //      bW[c+1] = T_c bW[c] T_c'  (stored in the bS buffer).
-template <int NB, int CPW, int SYS>
-__global__ void __launch_bounds__(128) boundary_unitary_kernel(const PhasedParams p) {
-  extern __shared__ double2 smem[];
-  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wl >= p.w_cnt) return;
-  const int w = p.w_off + wl;
-  const Lane L(threadIdx.x & 31);
+// CG: the chunk totals were written by other CTAs of the SAME launch (fused use below): read them through L2.
+template <int NB, bool CG> __device__ __forceinline__ CM<NB> cm_load_tot(const Lane& L, const double2* p) {
+  if (!CG) return cm_load<NB>(L, p);
+  CM<NB> x;
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const double2 r = __ldcg(p + ((i * NB + j) * 2 + 0) * 32 + L.lane);
+      const double2 m = __ldcg(p + ((i * NB + j) * 2 + 1) * 32 + L.lane);
+      x.re[i][j][0] = r.x; x.re[i][j][1] = r.y; x.im[i][j][0] = m.x; x.im[i][j][1] = m.y;
+    }
+  return x;
+}
+template <int NB, int CPW, int SYS, bool CG>
+__device__ __forceinline__ void boundary_unitary_chain(const PhasedParams& p, const Lane& L, int w, double* tb) {
   const Slot<CPW> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   constexpr int GS = 32 / CPW;
   constexpr int E = cm_elems<NB>();
-  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
   const int Cn = p.Cn;
   const double2* T = p.totT + (size_t)w * Cn * E;
-  CM<NB> Tn = cm_load<NB>(L, T + (size_t)(Cn > 1 ? 1 : 0) * E);               // loads run one chunk ahead of the products
-  CM<NB> Ut = transpose<NB>(L, cm_load<NB>(L, T), tb);                        // U^T after chunk 0
+  CM<NB> Tn = cm_load_tot<NB, CG>(L, T + (size_t)(Cn > 1 ? 1 : 0) * E);         // loads run one chunk ahead of the products
+  CM<NB> Ut = transpose<NB>(L, cm_load_tot<NB, CG>(L, T), tb);                  // U^T after chunk 0
   for (int c = 1; c < Cn; c++) {
     const CM<NB> Tc = Tn;
-    if (c + 1 < Cn) Tn = cm_load<NB>(L, T + (size_t)(c + 1) * E);
+    if (c + 1 < Cn) Tn = cm_load_tot<NB, CG>(L, T + (size_t)(c + 1) * E);
     Ut = mul_nt<NB>(Ut, Tc);                                                  // U^T T_c^T
   }
   double fom;
@@ -353,14 +361,23 @@ __global__ void __launch_bounds__(128) boundary_unitary_kernel(const PhasedParam
   if (sl.valid && (L.lane % GS) == 0) p.fomc[(size_t)sl.r * p.M + sl.k] = fom;
   double2* bW = p.bS + (size_t)w * (Cn + 1) * E;
   cm_store<NB>(L, bW, W);
-  Tn = cm_load<NB>(L, T);
+  Tn = cm_load_tot<NB, CG>(L, T);
   for (int c = 0; c + 1 < Cn; c++) {
     const CM<NB> Tc = Tn;
-    if (c + 2 < Cn) Tn = cm_load<NB>(L, T + (size_t)(c + 1) * E);
+    if (c + 2 < Cn) Tn = cm_load_tot<NB, CG>(L, T + (size_t)(c + 1) * E);
     const CM<NB> X = mul_nt<NB, true, false>(Tc, W);
     W = mul_nt<NB>(Tc, X);
     cm_store<NB>(L, bW + (size_t)(c + 1) * E, W);
   }
+}
+template <int NB, int CPW, int SYS>
+__global__ void __launch_bounds__(128) boundary_unitary_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  const int wl = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wl >= p.w_cnt) return;
+  const Lane L(threadIdx.x & 31);
+  double* tb = reinterpret_cast<double*>(smem) + (size_t)(threadIdx.x >> 5) * (NB * NB * 2 * TB_PLANE);
+  boundary_unitary_chain<NB, CPW, SYS, false>(p, L, p.w_off + wl, tb);
 }
 // K3u: warp (w, c): conjugation recursion over the chunk's slices with the trace-dots.
 template <int NB, int CPW, bool SH>
