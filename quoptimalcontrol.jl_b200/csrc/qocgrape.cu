@@ -1324,6 +1324,18 @@ static int multi_shard_launch(qoc_handle* h, int r, bool grad) {
   qoc_handle* sh = m->sub[r];
   const int gi = grad ? 1 : 0;
   const size_t nx = (size_t)h->d.R * h->NK, rowlen = (size_t)h->d.R * (h->NK + 1), row = (size_t)h->NK + 1;
+  if (sh->path != 1) {                    // D > 16: the GEMM pipeline synchronises its stream once per evaluation -> plain launches,
+    sh->pen_amp = h->pen_amp; sh->pen_var = h->pen_var;      // still concurrent across devices (one thread each)
+    if (cudaMemcpyAsync(sh->x, m->hx, nx * sizeof(double), cudaMemcpyHostToDevice, sh->stream) != cudaSuccess) { sh->err = "cudaMemcpyAsync (pulse)"; return QOC_ECUDA; }
+    int rc = enqueue_allreduce(sh, sh->x, sh->out, grad, sh->stream);
+    if (rc != QOC_OK) return rc;
+    if (r == 0) {
+      cudaError_t e = grad ? cudaMemcpyAsync(m->hout, sh->out, rowlen * sizeof(double), cudaMemcpyDeviceToHost, sh->stream)
+                           : cudaMemcpy2DAsync(m->hout, row * sizeof(double), sh->out, row * sizeof(double), sizeof(double), h->d.R, cudaMemcpyDeviceToHost, sh->stream);
+      if (e != cudaSuccess) { sh->err = "cudaMemcpyAsync (result)"; return QOC_ECUDA; }
+    }
+    return QOC_OK;
+  }
   if (!sh->mt_graph[gi]) {
     sh->pen_amp = h->pen_amp; sh->pen_var = h->pen_var;       // every shard applies them to its copy of the sum; the lead's is read
     const bool ok = capture_graph(sh, &sh->mt_graph[gi], &sh->mt_launches[gi], [&]() {
@@ -1444,7 +1456,7 @@ static int multi_create(qoc_handle** out, const qoc_desc& d, int ndev) {
   {  // threaded mode: distinct devices, warp-resident path, peer access both ways
     bool distinct = true;
     for (int a = 0; a < n; a++) for (int b = 0; b < a; b++) if (m->dev[a] == m->dev[b]) distinct = false;
-    bool want = distinct && m->use_graph && n <= QOC_MAX_RANKS;
+    bool want = distinct && n <= QOC_MAX_RANKS;
     if (const char* e = getenv("QOC_MULTI_THREADS")) want = want && atoi(e) != 0;      // A/B: fall back to the single multi-device graph
     if (want && multi_comm_setup(h) == QOC_OK) {
       m->threaded = true;

@@ -161,3 +161,31 @@ def test_native_slice_parallel(world):
     for rank, errs in res:
         for name, ef, eg in errs:
             assert ef < 1e-10 and eg < 1e-8, (rank, name, ef, eg)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("D,M", [(8, 37), (32, 5)])
+def test_threaded_multi_device_handle_on_distinct_gpus(D, M):
+    """Distinct device ordinals select the threaded mode of the multi-device handle (one launch thread per device, in-process
+    peer-memory all-reduce), for the warp-resident path and for the D > 16 GEMM pipeline."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import quoptimalcontrol_jl_b200 as qoc
+    from oracle import grape_oracle as orc
+    from conftest import assert_parity, random_system
+    K, N, T = 2, 20, 0.9
+    members = [random_system(D, K, seed=330 + k) for k in range(M)]
+    wts = np.random.default_rng(M).random(M) / M
+    devs = list(range(min(torch.cuda.device_count(), 4)))
+    with qoc.GrapeEvaluator(members, T, N, orc.STATE_TRANSFER, wts=wts, devices=devs, pure_state=False, penalty=(0.01, 0.02)) as ev:
+        for it in range(4):
+            x = np.random.default_rng(it).uniform(-1, 1, (K, N))
+            F, G = ev.eval(x)
+            F0, _ = ev.eval(x, want_grad=False)
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, x, T, orc.STATE_TRANSFER)
+        d = np.diff(x, axis=1)
+        Fp = 0.01 * np.sum(x ** 2) + 0.02 * np.sum(d ** 2)
+        Gp = 2 * 0.01 * x
+        Gp[:, :-1] -= 2 * 0.02 * d
+        Gp[:, 1:] += 2 * 0.02 * d
+        assert_parity(F, G, Fo + Fp, Go + Gp)
+        assert abs(F0 - (Fo + Fp)) < 1e-10
