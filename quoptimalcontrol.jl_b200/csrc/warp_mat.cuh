@@ -9,7 +9,10 @@
 // i.e. the tensor pipe natively computes the "NT" product  C = A * B^T  (or A * B^H) on row-distributed
 // registers and delivers C in the same layout: chains of products need NO fragment conversion.  The only data
 // movement left is an explicit transpose, done through a padded per-warp shared-memory tile
-// (2 STS.128 + 4 LDS.64 per complex 8x8 block, bank-conflict free, no selects).
+// (2 STS.128 + 4 LDS.64 per complex 8x8 block, no selects).  Row stride 10 doubles keeps the four column-wise LDS.64
+// conflict-free; the two row-wise STS.128 then cost one extra wavefront per quarter-warp (rows g and g+1 are 20 banks
+// apart, so their 16-bank footprints overlap by 4): ~17 M conflict wavefronts per cfg4 launch in ncu, <1 % of the LSU
+// traffic.  No stride serves both (stores want stride = 8 mod 16, which makes the loads 4-way conflicting).
 #pragma once
 #include <cuda_runtime.h>
 #include "params.h"
