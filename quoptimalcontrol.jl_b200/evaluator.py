@@ -120,6 +120,20 @@ class GrapeEvaluator:
         fn = self._lib.qoc_eval_allreduce if allreduce else self._lib.qoc_eval
         self._check(fn(self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data))
 
+    def raw_caller(self, xb, F, G=None, allreduce=False):
+        """eval_raw with the pointer marshalling done once: returns a zero-argument callable for tight loops (the per-call
+        Python cost is then one ctypes foreign call, as close as Python gets to the Julia `ccall`)."""
+        fn = self._lib.qoc_eval_allreduce if allreduce else self._lib.qoc_eval
+        h, px, pF, pG = self._h, xb.ctypes.data, F.ctypes.data, None if G is None else G.ctypes.data
+        keep = (xb, F, G)                      # the closure keeps the buffers alive
+
+        def call():
+            rc = fn(h, px, pF, pG)
+            if rc != _lib.QOC_OK:
+                self._check(rc)
+            return keep
+        return call
+
     def eval_device(self, x_dev_ptr, fg_dev_ptr, want_grad=True, stream=None):
         """Asynchronous evaluation on device pointers (ints): x [R][N][K], FG [R][1 + N*K]."""
         self._check(self._lib.qoc_eval_device(self._h, x_dev_ptr, fg_dev_ptr, int(want_grad), stream))
