@@ -27,7 +27,14 @@ for spec in sys.argv[1:] or ["512"]:
             e1.record(st); st.synchronize()
         s = ev.stats()
         out = fg.cpu().numpy()
+        import time
+        xb = np.ascontiguousarray(cfg["x"].T); Fh = np.empty(1); Gh = np.empty((N, K))
+        call = ev.raw_caller(xb, Fh, Gh)
+        for _ in range(5): call()
+        t0 = time.perf_counter()
+        for _ in range(200): call()
+        e2e_ms = (time.perf_counter() - t0) / 200 * 1e3
         if M not in ref: ref[M] = out
         dev = float(np.max(np.abs(out[1:] - ref[M][1:])) / np.max(np.abs(ref[M][1:])))
-        print(f"M={spec:>40s} step {e0.elapsed_time(e1)/reps:7.4f} ms  chain kernels {s['main_kernel_ms_avg']:7.4f} ms  launches {s['launches_last_eval']}  dev vs first {dev:.1e}", flush=True)
+        print(f"M={spec:>40s} step {e0.elapsed_time(e1)/reps:7.4f} ms  chain kernels {s['main_kernel_ms_avg']:7.4f} ms  launches {s['launches_last_eval']}  dev vs first {dev:.1e}  host-buffer call {e2e_ms:7.4f} ms (+{(e2e_ms - e0.elapsed_time(e1)/reps)*1e3:5.1f} us)", flush=True)
     for k in envs: os.environ.pop(k, None)
