@@ -194,3 +194,23 @@ def test_solve_ensemble_on_a_multi_device_algorithm():
     # the shard sums differ from the single-device sum in the last bits, so the two optimisation paths drift apart: compare
     # the minima they reach, not the trajectories
     assert a.fidelity < 0.7501 and b.fidelity < 0.7501 and abs(a.fidelity - b.fidelity) < 1e-4
+
+
+def test_one_rank_allreduce_with_several_pulses():
+    """R > 1 through the fused reduction + all-reduce kernel (rows [R][chunks][NK+1]) and through a multi-device handle."""
+    D, K, N, T, M, R = 8, 3, 70, 1.0, 160, 3
+    members = [random_system(D, K, seed=1200 + (k % 7), unitary_targets=True) for k in range(M)]
+    wts = np.random.default_rng(1).random(M) / M
+    xs = np.random.default_rng(2).uniform(-1, 1, (R, K, N))
+    with qoc.GrapeEvaluator(members, T, N, orc.UNITARY_GATE, wts=wts, n_pulses=R) as ev:
+        ev.comm_connect(1, 0, [ev.comm_export()])
+        for _ in range(2):
+            F, G = ev.eval_allreduce(xs)
+        Fr, Gr = ev.eval(xs)
+    with qoc.GrapeEvaluator(members, T, N, orc.UNITARY_GATE, wts=wts, n_pulses=R, devices=_devices(3)) as ev:
+        Fm, Gm = ev.eval(xs)
+    for r in range(R):
+        Fo, Go = orc.ensemble_fom_and_gradient(members, wts, xs[r], T, orc.UNITARY_GATE)
+        assert_parity(F[r], G[r], Fo, Go)
+        assert_parity(Fr[r], Gr[r], Fo, Go)
+        assert_parity(Fm[r], Gm[r], Fo, Go)
