@@ -510,6 +510,13 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
     if (dots_on_dmma && sweep_unitary_dmma_smem() > 48 * 1024)
       QOC_CUDA(h, cudaFuncSetAttribute((const void*)pick_sweep_unitary_dmma(), cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_unitary_dmma_smem()));
     const int parts = h->parts;
+    // QOC_TIMELINE=1 (tuning aid, plain-launch path only): CUDA-event end time of every kernel of every chain range,
+    // printed to stderr every 16th evaluation -- shows how long the dependent kernels wait for SM slots
+    static const bool timeline = getenv("QOC_TIMELINE") && atoi(getenv("QOC_TIMELINE")) != 0;
+    static cudaEvent_t tl[1 + 3 * qoc_handle::MAX_PARTS] = {};
+    const bool tl_on = timeline && !h->in_capture;
+    if (tl_on && !tl[0]) for (auto& e : tl) cudaEventCreate(&e);
+    if (tl_on) cudaEventRecord(tl[0], st);
     if (parts > 1) QOC_CUDA(h, cudaEventRecord(h->ev_fork, st));
     for (int i = 0; i < parts; i++) {                       // chains [w0, w1) on their own stream: expm -> boundary -> sweep
       cudaStream_t ps = i == 0 ? st : h->aux[i];
@@ -520,8 +527,10 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
       const unsigned gchunks = (unsigned)(((long)q.w_cnt * h->Cn + 3) / 4);
       k1<<<(unsigned)((long)q.w_cnt * ((h->Cn + 3) / 4)), 128, smem1_used, ps>>>(q);
       if ((rc = launch_check(h, "chunk_expm_kernel")) != QOC_OK) return rc;
+      if (tl_on) cudaEventRecord(tl[1 + 3 * i], ps);
       kb<<<(unsigned)((q.w_cnt + 3) / 4), 128, h->tb_bytes, ps>>>(q);
       if ((rc = launch_check(h, "boundary_unitary_kernel")) != QOC_OK) return rc;
+      if (tl_on) cudaEventRecord(tl[2 + 3 * i], ps);
       q.sys_in_smem = sweep_in_smem;
       if (dots_on_dmma) {
         pick_sweep_unitary_dmma()<<<(unsigned)((long)q.w_cnt * ((h->Cn + 3) / 4)), 128, sweep_unitary_dmma_smem(), ps>>>(q);
@@ -530,9 +539,23 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
         ks<<<gchunks, 128, smem3, ps>>>(q);
         if ((rc = launch_check(h, "sweep_unitary_kernel")) != QOC_OK) return rc;
       }
+      if (tl_on) cudaEventRecord(tl[3 + 3 * i], ps);
       if (i > 0) QOC_CUDA(h, cudaEventRecord(h->ev_join[i], ps));
     }
     for (int i = 1; i < parts; i++) QOC_CUDA(h, cudaStreamWaitEvent(st, h->ev_join[i], 0));
+    if (tl_on) {
+      static int shown = 0;
+      cudaStreamSynchronize(st);
+      if (shown++ % 16 == 8) {
+        fprintf(stderr, "[qoc timeline] %d chains x %d chunks, end times in us after the fork:", h->n_groups, h->Cn);
+        for (int i = 0; i < parts; i++) {
+          float a = 0, b = 0, c = 0;
+          cudaEventElapsedTime(&a, tl[0], tl[1 + 3 * i]); cudaEventElapsedTime(&b, tl[0], tl[2 + 3 * i]); cudaEventElapsedTime(&c, tl[0], tl[3 + 3 * i]);
+          fprintf(stderr, "  range %d: expm %.1f, boundary %.1f, sweep %.1f;", i, a * 1e3, b * 1e3, c * 1e3);
+        }
+        fprintf(stderr, "\n");
+      }
+    }
     return QOC_OK;
   }
   k1<<<(unsigned)((long)h->n_groups * ((h->Cn + 3) / 4)), 128, smem1_used, st>>>(p);
