@@ -50,4 +50,7 @@ phased_fn pick_chunk_expm_dmma() { return chunk_expm_dmma_kernel; }
 int chunk_expm_dmma_smem() { return (1024 + 4 * ASM_WARP_DOUBLES) * (int)sizeof(double); }
 phased_fn pick_sweep_unitary_dmma() { return sweep_unitary_dmma_kernel; }
 int sweep_unitary_dmma_smem() { return (1024 + 4 * 8 * DOT_LD) * (int)sizeof(double); }
+persist_fn pick_closed_persistent(int sys) { return sys == SYS_UNITARY ? closed_persistent_kernel<SYS_UNITARY> : closed_persistent_kernel<SYS_DENSITY>; }
+int closed_persistent_smem() { return (1024 + 4 * ASM_WARP_DOUBLES) * (int)sizeof(double); }
+int closed_persistent_ctl_ints(int n_groups, int Cn) { return persist_ctl_ints(n_groups, Cn); }
 }  // namespace qoc

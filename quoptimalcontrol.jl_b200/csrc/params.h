@@ -90,6 +90,12 @@ struct PhasedParams {
   double2* bC;             // [n_groups][Cn+1][E] chunk-boundary costates
   int sys_in_smem;
   int store_plain;         // chunk_expm_kernel stores P_t instead of P_t^T (closed-system mode)
+  // chunk_expm_dmma_item: when, over all members, at most 4 of the 1 + K scaled matrices (-i dt A, -i dt B_j) have a non-zero
+  // real plane and at most 4 a non-zero imaginary plane (Pauli-type controls: each is purely real or purely imaginary), every
+  // plane is assembled from its own coefficient list in ONE k-step: 16 instead of 32 DMMA per 8 slices.  Lists as 4 packed
+  // bytes (coefficient index 0 = drift, j = control j; 0xff = unused).
+  int asm_sparse;
+  unsigned asm_lr, asm_li;
   double* fomc;
   double* gradc;
 };
@@ -112,6 +118,12 @@ phased_fn pick_chunk_expm_dmma();         // D = 5..8 (NB = 1, one chain per war
 int chunk_expm_dmma_smem();
 phased_fn pick_sweep_unitary_dmma();     // D = 5..8 (NB = 1, one chain per warp), K <= 8: trace-dots on the tensor pipe
 int sweep_unitary_dmma_smem();           // its dynamic shared memory per CTA; grid = chains x ceil(Cn / 4)
+// persistent closed-system kernel (D = 5..8, 1 <= K <= 7): exponentials, boundary stage and sweeps of all chains in one launch,
+// CTA-sized work items pulled from device-memory queues; ctl = closed_persistent_ctl_ints() ints, zeroed before every launch
+typedef void (*persist_fn)(const PhasedParams, int*, int);
+persist_fn pick_closed_persistent(int sys);
+int closed_persistent_smem();
+int closed_persistent_ctl_ints(int n_groups, int Cn);
 // ---- launch wrappers of the non-template kernels (defined in k_small_fused.cu); return cudaGetLastError() ---------------
 cudaError_t launch_pack(const PackParams& pp, long total, cudaStream_t st);
 cudaError_t launch_reduce_pass1(const double* gradc, const double* fomc, const double* wts, double* part, int M, int NK, int R,

@@ -45,7 +45,13 @@ struct qoc_handle {
   int part_lo[MAX_PARTS + 1] = {};       // chain range of every part (later parts smaller: their boundary + sweep stages are the tail)
   cudaStream_t aux[MAX_PARTS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_PARTS] = {};
+  int asm_sparse = 0;                    // plane-wise generator assembly (PhasedParams::asm_sparse), decided in qoc_set_system
+  unsigned asm_lr = 0xffffffffu, asm_li = 0xffffffffu;
   int unitary_fast = 1;                  // closed-system conjugation kernel when the problem is Hermitian (QOC_UNITARY_FAST=0 disables)
+  // persistent closed-system kernel (small_phased.cuh): one launch, work items from device-memory queues (QOC_PERSIST=0 disables)
+  int persist = 0, persist_grid = 0, persist_reserve = 0;
+  int* persist_ctl = nullptr;
+  size_t persist_ctl_bytes = 0;
   double2 *bS = nullptr, *bC = nullptr;
   int NK = 0, red_chunk = 0, red_nchunks = 0;
   bool system_set = false;
@@ -232,6 +238,22 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
     CR(dev_alloc(h, &h->ident, (size_t)h->n_sysgroups * E));
     CR(dev_alloc(h, &h->storeP, (size_t)h->n_groups * d.N * E));
     if (!h->phased) CR(dev_alloc(h, &h->storeS, (size_t)h->n_groups * d.N * E));
+    if ((h->chunked || h->chunked_closed) && h->NB == 1 && h->CPW == 1 && d.K >= 1 && d.K <= 7 && d.gradient == QOC_GRAD_FIRST_ORDER) {
+      // measured 2-4 % slower than the three-launch form on cfg4 shards (profiles/README.md, r02q): opt-in
+      if (const char* e = getenv("QOC_PERSIST")) h->persist = atoi(e) != 0;
+      if (getenv("QOC_ASM_DMMA") && !atoi(getenv("QOC_ASM_DMMA"))) h->persist = 0;      // the A/B switches of the three-launch form
+      if (getenv("QOC_DOTS_DMMA") && !atoi(getenv("QOC_DOTS_DMMA"))) h->persist = 0;
+      if (h->persist) {
+        int sms = 0;
+        CRC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device));
+        const long items = (long)h->n_groups * ((h->Cn + 3) / 4);
+        h->persist_grid = (int)std::min<long>((long)sms * 5, items);
+        h->persist_reserve = h->persist_grid;                   // S items kept back for the tail (in units of items)
+        if (const char* e = getenv("QOC_PERSIST_RESERVE")) h->persist_reserve = (int)std::min<long>(1L << 30, std::max<long>(h->persist_grid, atol(e)));
+        h->persist_ctl_bytes = (size_t)closed_persistent_ctl_ints(h->n_groups, h->Cn) * sizeof(int);
+        CR(dev_alloc(h, (char**)&h->persist_ctl, h->persist_ctl_bytes));
+      }
+    }
     if (h->chunked || h->chunked_closed) {
       CR(dev_alloc(h, &h->totT, (size_t)h->n_groups * h->Cn * E));
       CR(dev_alloc(h, &h->totTt, (size_t)h->n_groups * h->Cn * E));
@@ -291,7 +313,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->comm_peers) cudaFree(h->comm_peers);
   if (h->comm_ctl) cudaFree(h->comm_ctl);
   slice_destroy(h);
-  void* bufs[] = {h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
+  void* bufs[] = {h->persist_ctl, h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hout) cudaFreeHost(h->hout);
@@ -356,6 +378,23 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
     for (int k = 0; k < nA && herm; k++) herm = is_herm(A + 2 * (size_t)k * DD);
     for (int k = 0; k < nB * d.K && herm; k++) herm = is_herm(B + 2 * (size_t)k * DD);
     h->herm = herm ? 1 : 0;
+    // which of the scaled matrices -i dt A, -i dt B_j have a non-zero real / imaginary plane in ANY member
+    // (real plane of -i dt X = dt Im X, imaginary plane = -dt Re X): coefficient lists of the plane-wise DMMA assembly
+    unsigned lr = 0xffffffffu, li = 0xffffffffu;
+    int nr = 0, ni = 0;
+    for (int j = 0; j <= d.K; j++) {
+      bool any_re = false, any_im = false;
+      const int nsrc = j == 0 ? nA : nB;
+      for (int k = 0; k < nsrc; k++) {
+        const double* Mx = j == 0 ? A + 2 * (size_t)k * DD : B + 2 * ((size_t)k * d.K + (j - 1)) * DD;
+        for (size_t e = 0; e < DD; e++) { any_re = any_re || Mx[2 * e] != 0.0; any_im = any_im || Mx[2 * e + 1] != 0.0; }
+      }
+      if (any_im) { if (nr < 4) lr = (lr & ~(0xffu << (8 * nr))) | ((unsigned)j << (8 * nr)); nr++; }
+      if (any_re) { if (ni < 4) li = (li & ~(0xffu << (8 * ni))) | ((unsigned)j << (8 * ni)); ni++; }
+    }
+    h->asm_sparse = nr <= 4 && ni <= 4;
+    if (const char* e = getenv("QOC_ASM_SPARSE")) h->asm_sparse = h->asm_sparse && atoi(e) != 0;      // A/B testing
+    h->asm_lr = lr; h->asm_li = li;
   }
   auto upload = [&](const double* src, size_t count) -> int {
     QOC_CUDA(h, cudaMemcpyAsync(h->staging, src, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
@@ -453,6 +492,7 @@ static PhasedParams phased_params(qoc_handle* h, const double* x_dev) {
   p.sys = h->sys; p.xi = h->xi; p.xt = h->xt; p.x = x_dev; p.storePt = h->storeP; p.storeP = h->storeP2; p.stS = h->stS; p.stC = h->stC;
   p.totT = h->totT; p.totTt = h->totTt; p.tau = h->tau; p.fomc = h->fomc; p.gradc = h->gradc;
   p.bS = h->bS; p.bC = h->bC; p.sys_in_smem = 0; p.store_plain = 0;
+  p.asm_sparse = h->asm_sparse; p.asm_lr = h->asm_lr; p.asm_li = h->asm_li;
   p.w_off = 0; p.w_cnt = h->n_groups;
   return p;
 }
@@ -509,6 +549,13 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
     if (const char* e = getenv("QOC_DOTS_DMMA")) dots_on_dmma = dots_on_dmma && atoi(e) != 0;      // A/B testing
     if (dots_on_dmma && sweep_unitary_dmma_smem() > 48 * 1024)
       QOC_CUDA(h, cudaFuncSetAttribute((const void*)pick_sweep_unitary_dmma(), cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_unitary_dmma_smem()));
+    if (h->persist && asm_on_dmma && dots_on_dmma) {        // one persistent launch instead of 3 per chain range
+      persist_fn kp = pick_closed_persistent(sys);
+      QOC_CUDA(h, cudaFuncSetAttribute((const void*)kp, cudaFuncAttributeMaxDynamicSharedMemorySize, closed_persistent_smem()));
+      QOC_CUDA(h, cudaMemsetAsync(h->persist_ctl, 0, h->persist_ctl_bytes, st));
+      kp<<<(unsigned)h->persist_grid, 128, closed_persistent_smem(), st>>>(p, h->persist_ctl, h->persist_reserve);
+      return launch_check(h, "closed_persistent_kernel");
+    }
     const int parts = h->parts;
     // QOC_TIMELINE=1 (tuning aid, plain-launch path only): CUDA-event end time of every kernel of every chain range,
     // printed to stderr every 16th evaluation -- shows how long the dependent kernels wait for SM slots

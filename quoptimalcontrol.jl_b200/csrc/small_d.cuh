@@ -59,6 +59,18 @@ __device__ __forceinline__ int scaling_power(float nrm, float theta) {
   return s > 60 ? 60 : s;
 }
 
+// The exponential itself uses the same scheme with the scalar factors moved so that the elementwise FP64 work per matrix
+// shrinks from 30 to 23 instructions (they share the pipe with the DMMAs):
+//   Yh = A + (x2/x1) A2 + (x3/x1) I;   Lh = A2 Yh = (A4 + x3 A2) / x1;   A4 = x1 Lh - x3 A2
+//   Rh = x1 (x4 I + x5 A + x6 A2 + x7 A4) = r4 I + r5 A + r6 A2 + r7 Lh;   T8 = I + A + y2 A2 + Lh Rh
+// (constants from the x_i above in 40-digit arithmetic; x2/x1 = 1/4, r5 = 11/630, r7 = 1/2520)
+constexpr double T8_YA = 0.25;
+constexpr double T8_YB = 6.1520673478250353627;
+constexpr double T8_R4 = 0.059249617736388271447;
+constexpr double T8_R5 = 0.017460317460317460317;
+constexpr double T8_R6 = -0.00091433916494050425595;
+constexpr double T8_R7 = 0.00039682539682539682538;
+
 // P = exp(G): scaling, T8 in 3 NT products, s squarings.  `herm`: G is anti-Hermitian (Hermitian drift and
 // controls, checked on the host), so G^T = -conj(G) and (G^2)^T = conj(G^2) cost no data movement.
 template <int NB> __device__ __forceinline__ CM<NB> expm_t8(const Lane& L, CM<NB> G, float theta, bool herm, double* tb) {
@@ -67,14 +79,13 @@ template <int NB> __device__ __forceinline__ CM<NB> expm_t8(const Lane& L, CM<NB
   const CM<NB> Gt = herm ? cm_negconj<NB>(G) : transpose<NB>(L, G, tb);
   const CM<NB> G2 = mul_nt<NB>(G, Gt);
   const CM<NB> G2t = herm ? cm_conj<NB>(G2) : transpose<NB>(L, G2, tb);
-  CM<NB> Y1t = cm_scale<NB>(Gt, T8_X1); cm_axpy<NB>(Y1t, T8_X2, G2t);
-  const CM<NB> G4 = mul_nt<NB>(G2, Y1t);
-  const CM<NB> G4t = transpose<NB>(L, G4, tb);
-  CM<NB> L8 = G4; cm_axpy<NB>(L8, T8_X3, G2);
-  CM<NB> R8t = cm_scale<NB>(Gt, T8_X5); cm_axpy<NB>(R8t, T8_X6, G2t); cm_axpy<NB>(R8t, T8_X7, G4t);
-  cm_add_identity<NB>(L, R8t, T8_X4);
+  CM<NB> Yht = Gt; cm_axpy<NB>(Yht, T8_YA, G2t); cm_add_identity<NB>(L, Yht, T8_YB);
+  const CM<NB> Lh = mul_nt<NB>(G2, Yht);
+  const CM<NB> Lht = transpose<NB>(L, Lh, tb);
+  CM<NB> Rht = cm_scale<NB>(Gt, T8_R5); cm_axpy<NB>(Rht, T8_R6, G2t); cm_axpy<NB>(Rht, T8_R7, Lht);
+  cm_add_identity<NB>(L, Rht, T8_R4);
   CM<NB> P = G; cm_axpy<NB>(P, T8_Y2, G2); cm_add_identity<NB>(L, P, 1.0);
-  mul_nt_acc<NB>(L8, R8t, P);
+  mul_nt_acc<NB>(Lh, Rht, P);
   for (int j = 0; j < s; j++) { const CM<NB> Pt = transpose<NB>(L, P, tb); P = mul_nt<NB>(P, Pt); }
   return P;
 }

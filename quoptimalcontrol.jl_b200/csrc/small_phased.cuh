@@ -427,16 +427,15 @@ __global__ void __launch_bounds__(128, NB == 1 ? QOC_SWEEP_MINB : 1) sweep_unita
 //                              the four warps of a CTA work on four chunks of the SAME chain
 //   Wb [8 slices][132]         per warp; row stride 132 doubles makes the fragment loads conflict-free
 constexpr int DOT_LD = 132;
-__global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const PhasedParams p) {
-  extern __shared__ double2 smem[];
+// One CTA-sized work item: chunks 4 cg .. 4 cg + 3 of chain w.  `Wstride`: doubles between the per-warp tiles.
+// CG: the boundary operator was written by another CTA of the SAME launch (persistent kernel): read it through L2.
+template <bool CG>
+__device__ __forceinline__ void sweep_unitary_dmma_item(const PhasedParams& p, double* Bd, int Wstride, int w, int cg) {
   constexpr int NB = 1;
   constexpr int E = cm_elems<NB>();
-  double* Bd = reinterpret_cast<double*>(smem);
   const int warp = threadIdx.x >> 5;
-  double* Wb = Bd + 1024 + warp * (8 * DOT_LD);
-  const int Cg = (p.Cn + 3) >> 2;
-  const int wl = blockIdx.x / Cg, cg = blockIdx.x - wl * Cg;
-  const int w = p.w_off + wl, c = cg * 4 + warp;
+  double* Wb = Bd + 1024 + warp * Wstride;
+  const int c = cg * 4 + warp;
   const Lane L(threadIdx.x & 31);
   const Slot<1> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   const int N = p.N, K = p.K;
@@ -452,7 +451,7 @@ __global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const Phased
   const int t0 = chunk_lo(c, N, p.Cn), t1 = chunk_lo(c + 1, N, p.Cn);
   const double2* stP = p.storePt + (size_t)w * N * E;      // holds P (not P^T) in this mode
   double* out = p.gradc + ((size_t)sl.r * p.M + sl.k) * N * K;
-  CM<NB> W = cm_load<NB>(L, p.bS + ((size_t)w * (p.Cn + 1) + c) * E);
+  CM<NB> W = cm_load_tot<NB, CG>(L, p.bS + ((size_t)w * (p.Cn + 1) + c) * E);
   CM<NB> Pn = cm_load<NB>(L, stP + (size_t)t0 * E);
   const int cc = L.g, tq = 2 * L.q;
   for (int tb = t0; tb < t1; tb += 8) {
@@ -485,6 +484,12 @@ __global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const Phased
     __syncwarp();
   }
 }
+__global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  const int Cg = (p.Cn + 3) >> 2;
+  const int wl = blockIdx.x / Cg;
+  sweep_unitary_dmma_item<false>(p, reinterpret_cast<double*>(smem), 8 * DOT_LD, p.w_off + wl, blockIdx.x - wl * Cg);
+}
 
 // K1 with the generator assembly on the tensor pipe (D = 5..8, one chain per warp, K <= 7).
 // G_t = A~ + sum_j x[j,t] B~_j costs 24 dependent DFMA + 14 LDS.128 per slice in scalar form; like the trace-dots of the sweep
@@ -496,25 +501,32 @@ __global__ void __launch_bounds__(128, 5) sweep_unitary_dmma_kernel(const Phased
 //   per warp: [28 spare][8 rows x DOT_LD]   the transpose tile of warp_mat.cuh (160 doubles) aliases the spare doubles + row 0,
 //                                           which is dead as soon as slice 0 of the batch sits in registers
 constexpr int ASM_WARP_DOUBLES = 28 + 8 * DOT_LD;
-__global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedParams p) {
-  extern __shared__ double2 smem[];
+// One CTA-sized work item: chunks 4 cg .. 4 cg + 3 of chain w.
+__device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, double* Ad, int w, int cg) {
   constexpr int NB = 1;
   constexpr int E = cm_elems<NB>();
-  double* Ad = reinterpret_cast<double*>(smem);
   const int warp = threadIdx.x >> 5;
   double* tile = Ad + 1024 + warp * ASM_WARP_DOUBLES;      // transpose tile (2 * TB_PLANE doubles) ...
   double* Gb = tile + 28;                                  // ... overlapping the first staging row
-  const int Cg = (p.Cn + 3) >> 2;
-  const int wl = blockIdx.x / Cg, cg = blockIdx.x - wl * Cg;
-  const int w = p.w_off + wl, c = cg * 4 + warp;
+  const int c = cg * 4 + warp;
   const Lane L(threadIdx.x & 31);
   const Slot<1> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   const int N = p.N, K = p.K;
+  const bool sparse = p.asm_sparse != 0;
+  const int jr = (int)((p.asm_lr >> (8 * L.q)) & 0xffu), ji = (int)((p.asm_li >> (8 * L.q)) & 0xffu);   // this lane's k index -> coefficient
   {
     const double* sysd = reinterpret_cast<const double*>(p.sys + (size_t)sl.sysgroup * p.nmat * E);
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-      const int ln = i & 31, ks = (i >> 5) & 1, mb = i >> 6, g = ln >> 2, q = ln & 3, j = 4 * ks + q;
-      Ad[i] = j <= K ? sysd[(size_t)j * (2 * E) + 8 * mb + g] : 0.0;
+    if (sparse) {       // Ad [16 m-blocks][32 lanes]: blocks 0..7 = real plane (list asm_lr), 8..15 = imaginary plane (asm_li)
+      for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        const int ln = i & 31, mb = i >> 5, g = ln >> 2, q = ln & 3;
+        const int j = (int)(((mb < 8 ? p.asm_lr : p.asm_li) >> (8 * q)) & 0xffu);
+        Ad[i] = j <= K ? sysd[(size_t)j * (2 * E) + 8 * mb + g] : 0.0;
+      }
+    } else {
+      for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        const int ln = i & 31, ks = (i >> 5) & 1, mb = i >> 6, g = ln >> 2, q = ln & 3, j = 4 * ks + q;
+        Ad[i] = j <= K ? sysd[(size_t)j * (2 * E) + 8 * mb + g] : 0.0;
+      }
     }
   }
   __syncthreads();
@@ -528,16 +540,27 @@ __global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedPar
     {  // X fragments: lane (g = slice, q): k-step 0 -> (1, x_1, x_2, x_3)[q], k-step 1 -> x_{4+q}
       const int ts = min(tb + L.g, t1 - 1);
       const double* xs = xr + (size_t)ts * K;
-      const double b0 = L.q == 0 ? 1.0 : (L.q <= K ? __ldg(xs + L.q - 1) : 0.0);
-      const double b1 = 4 + L.q <= K ? __ldg(xs + 3 + L.q) : 0.0;
       const double* ap = Ad + L.lane;
       double* gp = Gb + (2 * L.q) * DOT_LD + L.g;
+      if (sparse) {
+        const double br = jr == 0 ? 1.0 : (jr <= K ? __ldg(xs + jr - 1) : 0.0);
+        const double bi = ji == 0 ? 1.0 : (ji <= K ? __ldg(xs + ji - 1) : 0.0);
 #pragma unroll
-      for (int mb = 0; mb < 16; mb++) {
-        double d0 = 0.0, d1 = 0.0;
-        dmma(d0, d1, ap[(2 * mb) * 32], b0);
-        dmma(d0, d1, ap[(2 * mb + 1) * 32], b1);
-        gp[8 * mb] = d0; gp[8 * mb + DOT_LD] = d1;
+        for (int mb = 0; mb < 16; mb++) {
+          double d0 = 0.0, d1 = 0.0;
+          dmma(d0, d1, ap[mb * 32], mb < 8 ? br : bi);
+          gp[8 * mb] = d0; gp[8 * mb + DOT_LD] = d1;
+        }
+      } else {
+        const double b0 = L.q == 0 ? 1.0 : (L.q <= K ? __ldg(xs + L.q - 1) : 0.0);
+        const double b1 = 4 + L.q <= K ? __ldg(xs + 3 + L.q) : 0.0;
+#pragma unroll
+        for (int mb = 0; mb < 16; mb++) {
+          double d0 = 0.0, d1 = 0.0;
+          dmma(d0, d1, ap[(2 * mb) * 32], b0);
+          dmma(d0, d1, ap[(2 * mb + 1) * 32], b1);
+          gp[8 * mb] = d0; gp[8 * mb + DOT_LD] = d1;
+        }
       }
     }
     __syncwarp();
@@ -564,6 +587,101 @@ __global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedPar
   }
   if (!p.store_plain) cm_store<NB>(L, p.totTt + ((size_t)w * p.Cn + c) * E, Tt);
   cm_store<NB>(L, p.totT + ((size_t)w * p.Cn + c) * E, transpose<NB>(L, Tt, tile));
+}
+__global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedParams p) {
+  extern __shared__ double2 smem[];
+  const int Cg = (p.Cn + 3) >> 2;
+  const int wl = blockIdx.x / Cg;
+  chunk_expm_dmma_item(p, reinterpret_cast<double*>(smem), p.w_off + wl, blockIdx.x - wl * Cg);
+}
+
+// ---- persistent closed-system kernel: K1 + K2u + K3u of ALL chains in ONE launch -----------------------------------------
+// The three-launch form leaves SM slots idle at every kernel boundary: the exponential CTAs of a chain range live ~70 us, the
+// 10 us boundary kernel behind them waits for free slots, and the sweeps cannot start before it (profiles/r02p_shard_timeline.txt:
+// a 512-chain shard runs 0.297 ms against 0.257 ms of work).  Here 5 CTAs per SM stay resident and pull CTA-sized work items
+// from device-memory queues until everything is done:
+//   E (chain, 4 chunks)  exponentials + chunk totals (chunk_expm_dmma_item).  The CTA that finishes the LAST E item of a chain
+//                        (per-chain counter) runs the chain's boundary stage -- U_N, figure of merit, W_0, chunk-boundary
+//                        operators (boundary_unitary_chain) -- and appends the chain's S items to the S list
+//   S (chain, 4 chunks)  conjugation recursion + trace-dots (sweep_unitary_dmma_item)
+// E items go first (long items first: the short S items fill the tail), except that S items are taken early while more than
+// `reserve` of them are waiting (E and S work mixed on an SM use the FP64 pipe better than either alone, and a chain's
+// propagators are re-read while they still sit in L2).  Both queues are ticket
+// counters (one atomicAdd per item; a compare-and-swap claim serialises: one winner per L2 round trip, measured 0.7 us per
+// item).  An S ticket may be drawn before its entry is published; the holder waits for it.  That wait cannot deadlock: S
+// tickets are drawn only once every E item has been claimed, and every unpublished entry depends only on E items that
+// resident CTAs are executing.  A list entry is (id + 1); the whole control block is zeroed by ONE memset node before the
+// launch.  Data written by other CTAs of the launch (chunk totals, boundary operators) is read with ld.global.cg after a
+// fence; P_t is read once per launch, so no stale L1 line can exist.
+struct PersistCtl { int e_next, s_head, s_tail, pad[5]; };
+__device__ __forceinline__ int ld_vol(const int* q) { return *reinterpret_cast<const volatile int*>(q); }
+__device__ __forceinline__ void st_vol(int* q, int v) { *reinterpret_cast<volatile int*>(q) = v; }
+inline int persist_ctl_ints(int n_groups, int Cn) { return 8 + n_groups + n_groups * ((Cn + 3) / 4); }
+
+template <int SYS>
+__global__ void __launch_bounds__(128, 5) closed_persistent_kernel(const PhasedParams p, int* ctl_raw, int reserve) {
+  extern __shared__ double2 smem[];
+  __shared__ int sh_item[2];
+  double* smd = reinterpret_cast<double*>(smem);
+  const int Cg = (p.Cn + 3) >> 2;
+  const int nE = p.n_groups * Cg;
+  PersistCtl* ctl = reinterpret_cast<PersistCtl*>(ctl_raw);
+  int* chain_cnt = ctl_raw + 8;
+  int* s_ready = chain_cnt + p.n_groups;
+  bool e_done = false;                                       // meaningful in thread 0 only
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int a = -1;                                            // >= 0: E item a;  < -1: S item -(a + 2);  -1: exit
+      bool take_s = false;
+      if (!e_done) {
+        // mixing: an S item is taken early when more than `reserve` of them are waiting (reserve >= gridDim.x, so the ticket
+        // drawn below is certainly one of the published ones); the reserve itself stays for the tail
+        take_s = ld_vol(&ctl->s_tail) - ld_vol(&ctl->s_head) > reserve;
+        if (!take_s) {
+          a = atomicAdd(&ctl->e_next, 1);
+          if (a >= nE) { e_done = true; a = -1; }
+        }
+      }
+      if (e_done || take_s) {
+        const int j = atomicAdd(&ctl->s_head, 1);
+        if (j < nE) {
+          int v;
+          unsigned backoff = 32;
+          while ((v = ld_vol(s_ready + j)) == 0) { __nanosleep(backoff); if (backoff < 256) backoff <<= 1; }
+          __threadfence();
+          a = -(v - 1) - 2;
+        }
+      }
+      sh_item[0] = a;
+    }
+    __syncthreads();
+    const int a = sh_item[0];
+    if (a == -1) return;
+    if (a >= 0) {
+      const int w = a / Cg;
+      chunk_expm_dmma_item(p, smd, w, a - w * Cg);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) sh_item[1] = atomicAdd(&chain_cnt[w], 1) == Cg - 1;      // this CTA finished the chain's last E item
+      __syncthreads();
+      if (sh_item[1] && threadIdx.x < 32) {
+        const Lane L(threadIdx.x);
+        __threadfence();
+        boundary_unitary_chain<1, 1, SYS, true>(p, L, w, smd + 1024);
+        __threadfence();
+        __syncwarp();
+        if (L.lane == 0) {
+          const int slot = atomicAdd(&ctl->s_tail, Cg);
+          for (int i = 0; i < Cg; i++) st_vol(s_ready + slot + i, w * Cg + i + 1);
+        }
+      }
+    } else {
+      const int item = -(a + 2);
+      const int w = item / Cg;
+      sweep_unitary_dmma_item<true>(p, smd, ASM_WARP_DOUBLES, w, item - w * Cg);
+    }
+    __syncthreads();                                          // the shared tiles and sh_item are reused by the next item
+  }
 }
 
 }  // namespace qoc

@@ -72,7 +72,7 @@ def test_cfg4_full_timed_strategy():
     K, N = cfg["x"].shape
     with qoc.GrapeEvaluator(cfg["members"], cfg["T"], N, cfg["sys_type"], wts=cfg["wts"]) as ev:
         F, G = ev.eval(cfg["x"])
-        assert ev.stats()["launches_last_eval"] >= 5          # (chunk_expm, boundary_unitary, sweep_unitary) per chain range + reduce pass 1 + 2
+        assert ev.stats()["launches_last_eval"] >= 3          # closed_persistent_kernel + reduce pass 1 + 2 (three-launch form: 3 per chain range + 2)
         assert_parity(F, G, Fo, Go)
         F0, _ = ev.eval(cfg["x"], want_grad=False)
         assert_parity(F0, None, Fo, None)
