@@ -120,7 +120,7 @@ phased_fn pick_sweep_unitary_dmma();     // D = 5..8 (NB = 1, one chain per warp
 int sweep_unitary_dmma_smem();           // its dynamic shared memory per CTA; grid = chains x ceil(Cn / 4)
 // persistent closed-system kernel (D = 5..8, 1 <= K <= 7): exponentials, boundary stage and sweeps of all chains in one launch,
 // CTA-sized work items pulled from device-memory queues; ctl = closed_persistent_ctl_ints() ints, zeroed before every launch
-typedef void (*persist_fn)(const PhasedParams, int*, int);
+typedef void (*persist_fn)(const PhasedParams, int*, int, unsigned long long*);
 persist_fn pick_closed_persistent(int sys);
 int closed_persistent_smem();
 int closed_persistent_ctl_ints(int n_groups, int Cn);

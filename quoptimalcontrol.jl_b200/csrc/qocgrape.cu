@@ -553,8 +553,31 @@ static int eval_chunked(qoc_handle* h, SmallParams cp, const double* x_dev, int 
       persist_fn kp = pick_closed_persistent(sys);
       QOC_CUDA(h, cudaFuncSetAttribute((const void*)kp, cudaFuncAttributeMaxDynamicSharedMemorySize, closed_persistent_smem()));
       QOC_CUDA(h, cudaMemsetAsync(h->persist_ctl, 0, h->persist_ctl_bytes, st));
-      kp<<<(unsigned)h->persist_grid, 128, closed_persistent_smem(), st>>>(p, h->persist_ctl, h->persist_reserve);
-      return launch_check(h, "closed_persistent_kernel");
+      // QOC_PERSIST_TRACE=<file> (tuning aid, plain-launch path): per-item begin / end times of one evaluation
+      static const char* trace_path = getenv("QOC_PERSIST_TRACE");
+      unsigned long long* trace = nullptr;
+      const size_t trace_words = 4 + 4 * (2 * (size_t)h->n_groups * ((h->Cn + 3) / 4));
+      if (trace_path && !h->in_capture) {
+        QOC_CUDA(h, cudaMalloc((void**)&trace, trace_words * sizeof(unsigned long long)));
+        QOC_CUDA(h, cudaMemsetAsync(trace, 0, trace_words * sizeof(unsigned long long), st));
+      }
+      kp<<<(unsigned)h->persist_grid, 128, closed_persistent_smem(), st>>>(p, h->persist_ctl, h->persist_reserve, trace);
+      if ((rc = launch_check(h, "closed_persistent_kernel")) != QOC_OK) return rc;
+      if (trace) {
+        std::vector<unsigned long long> host(trace_words);
+        QOC_CUDA(h, cudaStreamSynchronize(st));
+        QOC_CUDA(h, cudaMemcpy(host.data(), trace, trace_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        if (FILE* f = fopen(trace_path, "w")) {
+          fprintf(f, "# kind(1=E,3=S) cta sm item begin_ns end_ns   chains=%d chunks=%d grid=%d\n", h->n_groups, h->Cn, h->persist_grid);
+          for (unsigned long long i = 0; i < host[0]; i++) {
+            const unsigned long long* r = host.data() + 4 + 4 * i;
+            fprintf(f, "%llu %llu %llu %llu %llu %llu\n", r[0] & 0xff, (r[0] >> 8) & 0xffffff, r[0] >> 32, r[1], r[2], r[3]);
+          }
+          fclose(f);
+        }
+      }
+      return QOC_OK;
     }
     const int parts = h->parts;
     // QOC_TIMELINE=1 (tuning aid, plain-launch path only): CUDA-event end time of every kernel of every chain range,

@@ -25,8 +25,8 @@ constexpr double T8_Y2 = 0.13549236135285063166;
 
 
 
-// 1-norm upper bound (column sums of |re|+|im|), warp-uniform max over all packed chains; float is enough
-// for a scaling decision and is rounded up.
+// Norm upper bound for the scaling decision (sums of |re|+|im|: rows = infinity norm, QOC_NORM_INF=0: columns = 1-norm),
+// warp-uniform max over all packed chains; float is enough for a scaling decision and is rounded up.
 // float upper bound of |x| from the high word of the double, on the integer pipe (the FP64 pipe is the
 // bottleneck resource): exponent re-biased by 1023-127 = 896, 20 mantissa bits kept, rounded up.
 __device__ __forceinline__ float abs_upper_f32(double x) {
@@ -35,7 +35,30 @@ __device__ __forceinline__ float abs_upper_f32(double x) {
   e = e < 0 ? 0 : (e > 0x0fdfffff ? 0x0fdfffff : e);
   return __int_as_float((e << 3) + 8);
 }
+#ifndef QOC_NORM_INF
+#define QOC_NORM_INF 1
+#endif
 template <int NB> __device__ __forceinline__ float cm_norm1_bound(const CM<NB>& x) {
+#if QOC_NORM_INF
+  // infinity norm (row sums): any induced norm serves the Taylor bound, and in the register layout a row lives in the four
+  // lanes of a quad, so a row sum needs 2 shuffles and the maximum over the rows 3 (column sums: 3 per column pair + 2)
+  float best = 0.f;
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) s += abs_upper_f32(x.re[i][j][e]) + abs_upper_f32(x.im[i][j][e]);
+    s += __shfl_xor_sync(FULL_MASK, s, 1);
+    s += __shfl_xor_sync(FULL_MASK, s, 2);
+    best = fmaxf(best, s);
+  }
+  best = fmaxf(best, __shfl_xor_sync(FULL_MASK, best, 4));
+  best = fmaxf(best, __shfl_xor_sync(FULL_MASK, best, 8));
+  best = fmaxf(best, __shfl_xor_sync(FULL_MASK, best, 16));
+  return best * 1.000001f;
+#else
   float best = 0.f;
 #pragma unroll
   for (int j = 0; j < NB; j++)
@@ -52,6 +75,7 @@ template <int NB> __device__ __forceinline__ float cm_norm1_bound(const CM<NB>& 
   best = fmaxf(best, __shfl_xor_sync(FULL_MASK, best, 1));
   best = fmaxf(best, __shfl_xor_sync(FULL_MASK, best, 2));
   return best * 1.000001f;
+#endif
 }
 __device__ __forceinline__ int scaling_power(float nrm, float theta) {
   if (!(nrm > theta)) return 0;

@@ -16,6 +16,14 @@
 #ifndef QOC_EXPM_MINB
 #define QOC_EXPM_MINB 5
 #endif
+// A/B switches of the exponential work item (profiles/README.md, r02s): deferred chunk-total update (measured slower:
+// 1.934 vs 1.902 ms at 4096 chains, off), pulse prefetch one batch ahead (neutral, on)
+#ifndef QOC_E_DEFER
+#define QOC_E_DEFER 0
+#endif
+#ifndef QOC_E_XPRE
+#define QOC_E_XPRE 1
+#endif
 #ifndef QOC_SWEEP_MINB
 #define QOC_SWEEP_MINB 6
 #endif
@@ -535,25 +543,42 @@ __device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, doub
   const double* xr = p.x + (size_t)sl.r * N * K;
   double2* stP = p.storePt + (size_t)w * N * E;
   CM<NB> Tt;
+#if QOC_E_DEFER
+  CM<NB> Pprev;                     // the chunk-total update of slice t is issued at the start of slice t + 1 (see below)
+#endif
+  // X fragments of a batch of 8 slices: lane (g = slice, q): dense: k-step 0 -> (1, x_1, x_2, x_3)[q], k-step 1 -> x_{4+q};
+  // plane-wise: real-plane list entry q, imaginary-plane list entry q.  Loaded one batch ahead (an L2 round trip per batch
+  // would otherwise sit on every warp's critical path).
+  auto load_x = [&](int tb, double& f0, double& f1) {
+    const int ts = min(tb + L.g, t1 - 1);
+    const double* xs = xr + (size_t)ts * K;
+    if (sparse) {
+      f0 = jr == 0 ? 1.0 : (jr <= K ? __ldg(xs + jr - 1) : 0.0);
+      f1 = ji == 0 ? 1.0 : (ji <= K ? __ldg(xs + ji - 1) : 0.0);
+    } else {
+      f0 = L.q == 0 ? 1.0 : (L.q <= K ? __ldg(xs + L.q - 1) : 0.0);
+      f1 = 4 + L.q <= K ? __ldg(xs + 3 + L.q) : 0.0;
+    }
+  };
+  double xn0, xn1;
+  load_x(t0, xn0, xn1);
   for (int tb = t0; tb < t1; tb += 8) {
     const int nb = min(8, t1 - tb);
-    {  // X fragments: lane (g = slice, q): k-step 0 -> (1, x_1, x_2, x_3)[q], k-step 1 -> x_{4+q}
-      const int ts = min(tb + L.g, t1 - 1);
-      const double* xs = xr + (size_t)ts * K;
+    {
+      const double b0 = xn0, b1 = xn1;
+#if QOC_E_XPRE
+      if (tb + 8 < t1) load_x(tb + 8, xn0, xn1);
+#endif
       const double* ap = Ad + L.lane;
       double* gp = Gb + (2 * L.q) * DOT_LD + L.g;
       if (sparse) {
-        const double br = jr == 0 ? 1.0 : (jr <= K ? __ldg(xs + jr - 1) : 0.0);
-        const double bi = ji == 0 ? 1.0 : (ji <= K ? __ldg(xs + ji - 1) : 0.0);
 #pragma unroll
         for (int mb = 0; mb < 16; mb++) {
           double d0 = 0.0, d1 = 0.0;
-          dmma(d0, d1, ap[mb * 32], mb < 8 ? br : bi);
+          dmma(d0, d1, ap[mb * 32], mb < 8 ? b0 : b1);
           gp[8 * mb] = d0; gp[8 * mb + DOT_LD] = d1;
         }
       } else {
-        const double b0 = L.q == 0 ? 1.0 : (L.q <= K ? __ldg(xs + L.q - 1) : 0.0);
-        const double b1 = 4 + L.q <= K ? __ldg(xs + 3 + L.q) : 0.0;
 #pragma unroll
         for (int mb = 0; mb < 16; mb++) {
           double d0 = 0.0, d1 = 0.0;
@@ -562,6 +587,9 @@ __device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, doub
           gp[8 * mb] = d0; gp[8 * mb + DOT_LD] = d1;
         }
       }
+#if !QOC_E_XPRE
+      if (tb + 8 < t1) load_x(tb + 8, xn0, xn1);
+#endif
     }
     __syncwarp();
     for (int i = 0; i < nb; i++) {
@@ -573,10 +601,20 @@ __device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, doub
         G.re[0][0][0] = r.x; G.re[0][0][1] = r.y; G.im[0][0][0] = m.x; G.im[0][0][1] = m.y;
       }
       __syncwarp();                                           // row 0 may now be overwritten by the transposes
+#if QOC_E_DEFER
+      // closed-system mode: the chunk-total product of the PREVIOUS slice is independent of this slice's norm estimate and
+      // first product, so its DMMAs fill the shuffle latency of the estimate (in-order issue: a warp has nothing else to issue)
+      if (p.store_plain && t > t0 + 1) Tt = mul_nt<NB>(Tt, Pprev);
+#endif
       const CM<NB> P = expm_t8<NB>(L, G, (float)p.theta, p.herm, tile);
       if (p.store_plain) {
         cm_store<NB>(L, stP + (size_t)t * E, P);
+#if QOC_E_DEFER
+        if (t == t0) Tt = transpose<NB>(L, P, tile);
+        Pprev = P;
+#else
         if (t == t0) Tt = transpose<NB>(L, P, tile); else Tt = mul_nt<NB>(Tt, P);
+#endif
       } else {
         const CM<NB> Pt = transpose<NB>(L, P, tile);
         cm_store<NB>(L, stP + (size_t)t * E, Pt);
@@ -585,6 +623,9 @@ __device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, doub
     }
     __syncwarp();
   }
+#if QOC_E_DEFER
+  if (p.store_plain && t1 - 1 > t0) Tt = mul_nt<NB>(Tt, Pprev);
+#endif
   if (!p.store_plain) cm_store<NB>(L, p.totTt + ((size_t)w * p.Cn + c) * E, Tt);
   cm_store<NB>(L, p.totT + ((size_t)w * p.Cn + c) * E, transpose<NB>(L, Tt, tile));
 }
@@ -616,10 +657,11 @@ __global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedPar
 struct PersistCtl { int e_next, s_head, s_tail, pad[5]; };
 __device__ __forceinline__ int ld_vol(const int* q) { return *reinterpret_cast<const volatile int*>(q); }
 __device__ __forceinline__ void st_vol(int* q, int v) { *reinterpret_cast<volatile int*>(q) = v; }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 inline int persist_ctl_ints(int n_groups, int Cn) { return 8 + n_groups + n_groups * ((Cn + 3) / 4); }
 
 template <int SYS>
-__global__ void __launch_bounds__(128, 5) closed_persistent_kernel(const PhasedParams p, int* ctl_raw, int reserve) {
+__global__ void __launch_bounds__(128, 5) closed_persistent_kernel(const PhasedParams p, int* ctl_raw, int reserve, unsigned long long* trace) {
   extern __shared__ double2 smem[];
   __shared__ int sh_item[2];
   double* smd = reinterpret_cast<double*>(smem);
@@ -657,6 +699,8 @@ __global__ void __launch_bounds__(128, 5) closed_persistent_kernel(const PhasedP
     __syncthreads();
     const int a = sh_item[0];
     if (a == -1) return;
+    unsigned long long t_begin = 0;
+    if (trace && threadIdx.x == 0) t_begin = global_ns();
     if (a >= 0) {
       const int w = a / Cg;
       chunk_expm_dmma_item(p, smd, w, a - w * Cg);
@@ -681,6 +725,16 @@ __global__ void __launch_bounds__(128, 5) closed_persistent_kernel(const PhasedP
       sweep_unitary_dmma_item<true>(p, smd, ASM_WARP_DOUBLES, w, item - w * Cg);
     }
     __syncthreads();                                          // the shared tiles and sh_item are reused by the next item
+    if (trace && threadIdx.x == 0) {                          // QOC_PERSIST_TRACE: (kind, CTA, SM), item, begin, end [ns]
+      const unsigned long long t_end = global_ns();
+      const unsigned long long slot = atomicAdd(trace, 1ULL);
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* r = trace + 4 + 4 * slot;
+      r[0] = (a >= 0 ? 1ULL : 3ULL) | ((unsigned long long)blockIdx.x << 8) | ((unsigned long long)smid << 32);
+      r[1] = (unsigned long long)(a >= 0 ? a : -(a + 2));
+      r[2] = t_begin; r[3] = t_end;
+    }
   }
 }
 
