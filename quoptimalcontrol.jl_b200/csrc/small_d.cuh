@@ -101,7 +101,7 @@ template <int NB> __device__ __forceinline__ CM<NB> expm_t8(const Lane& L, CM<NB
   const int s = scaling_power(cm_norm1_bound<NB>(G), theta);
   if (s) G = cm_scale<NB>(G, scalbn(1.0, -s));
   const CM<NB> Gt = herm ? cm_negconj<NB>(G) : transpose<NB>(L, G, tb);
-  const CM<NB> G2 = mul_nt<NB>(G, Gt);
+  const CM<NB> G2 = herm ? square_antiherm<NB>(G) : mul_nt<NB>(G, Gt);
   const CM<NB> G2t = herm ? cm_conj<NB>(G2) : transpose<NB>(L, G2, tb);
   CM<NB> Yht = Gt; cm_axpy<NB>(Yht, T8_YA, G2t); cm_add_identity<NB>(L, Yht, T8_YB);
   const CM<NB> Lh = mul_nt<NB>(G2, Yht);
@@ -289,8 +289,7 @@ __device__ __forceinline__ void chain_body(const SmallParams& p, double2* smem) 
     if (SYS == SYS_UNITARY) {
       S = mul_nt<NB>(S, P);                                       // S^T P^T          (GRAPE.jl:226)
     } else {
-      const CM<NB> X = mul_nt<NB, true, false>(P, S);             // conj(P) S^T = (S P')^T   (GRAPE.jl:245)
-      S = mul_nt<NB>(P, X);                                       // P (S P')         (GRAPE.jl:246)
+      S = conj_by<NB>(P, S);                                      // P (S P'): X = conj(P) S^T = (S P')^T, then nt(P, X)   (GRAPE.jl:245-246)
     }
   }
   // xt packed transposed for unitary, so elementwise overlaps with S are consistent in both cases
@@ -489,8 +488,7 @@ __device__ __forceinline__ void chain_body_unitary(const SmallParams& p, double2
     if (t + 1 < N) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
     emit_gradient<NB, CPW, SH, true>(p, L, sl, Bmats, W, t);
     if (t + 1 < N) {
-      const CM<NB> X = mul_nt<NB, true, false>(P, W);           // conj(P) W^T = (W P')^T
-      W = mul_nt<NB>(P, X);                                     // P W P'
+      W = conj_by<NB>(P, W);                                    // P W P'
     }
   }
 }

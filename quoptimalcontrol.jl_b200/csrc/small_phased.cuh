@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(128) boundary_kernel(const PhasedParams p) {
     for (int c = 0; c < Cn - 1; c++) {       // the last boundary (S_N) is produced by the sweep itself
       const CM<NB> T = cm_load<NB>(L, p.totT + ((size_t)w * Cn + c) * E);
       if (SYS == SYS_UNITARY) S = mul_nt<NB>(S, T);
-      else { const CM<NB> X = mul_nt<NB, true, false>(T, S); S = mul_nt<NB>(T, X); }
+      else S = conj_by<NB>(T, S);
       cm_store<NB>(L, st + (size_t)chunk_lo(c + 1, N, Cn) * E, S);
     }
   } else {
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(128) sweep_kernel(const PhasedParams p) {
           const CM<NB> P = ring[i];
           if (t + PF < t1) ring[i] = cm_load<NB>(L, Pm + (size_t)(t + PF) * E);
           if (SYS == SYS_UNITARY) S = mul_nt<NB>(S, P);
-          else { const CM<NB> X = mul_nt<NB, true, false>(P, S); S = mul_nt<NB>(P, X); }
+          else S = conj_by<NB>(P, S);
           if (t + 1 < t1 || c == Cn - 1) cm_store<NB>(L, st + (size_t)(t + 1) * E, S);
         }
       }
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128) boundary2_kernel(const PhasedParams p) {
     for (int c = 0; c < Cn; c++) {
       const CM<NB> T = cm_load<NB>(L, p.totT + ((size_t)w * Cn + c) * E);
       if (SYS == SYS_UNITARY) S = mul_nt<NB>(S, T);
-      else { const CM<NB> X = mul_nt<NB, true, false>(T, S); S = mul_nt<NB>(T, X); }
+      else S = conj_by<NB>(T, S);
       cm_store<NB>(L, st + (size_t)(c + 1) * E, S);
     }
     const CM<NB> Xt = cm_load<NB>(L, p.xt + (size_t)sl.sysgroup * E);
@@ -373,8 +373,7 @@ __device__ __forceinline__ void boundary_unitary_chain(const PhasedParams& p, co
   for (int c = 0; c + 1 < Cn; c++) {
     const CM<NB> Tc = Tn;
     if (c + 2 < Cn) Tn = cm_load_tot<NB, CG>(L, T + (size_t)(c + 1) * E);
-    const CM<NB> X = mul_nt<NB, true, false>(Tc, W);
-    W = mul_nt<NB>(Tc, X);
+    W = conj_by<NB>(Tc, W);
     cm_store<NB>(L, bW + (size_t)(c + 1) * E, W);
   }
 }
@@ -414,7 +413,7 @@ __device__ __forceinline__ void sweep_unitary_body(const PhasedParams& p, double
     const CM<NB> P = Pn;
     if (t + 1 < t1) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
     emit_gradient<NB, CPW, SH, true>(sp, L, sl, Bmats, W, t);
-    if (t + 1 < t1) { const CM<NB> X = mul_nt<NB, true, false>(P, W); W = mul_nt<NB>(P, X); }
+    if (t + 1 < t1) W = conj_by<NB>(P, W);
   }
 }
 template <int NB, int CPW>
@@ -471,7 +470,7 @@ __device__ __forceinline__ void sweep_unitary_dmma_item(const PhasedParams& p, d
       double* row = Wb + i * DOT_LD + 2 * L.lane;
       *reinterpret_cast<double2*>(row) = make_double2(W.re[0][0][0], W.re[0][0][1]);
       *reinterpret_cast<double2*>(row + 64) = make_double2(W.im[0][0][0], W.im[0][0][1]);
-      if (t + 1 < t1) { const CM<NB> X = mul_nt<NB, true, false>(P, W); W = mul_nt<NB>(P, X); }
+      if (t + 1 < t1) W = conj_by<NB>(P, W);
     }
     __syncwarp();
     double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;      // four accumulator chains

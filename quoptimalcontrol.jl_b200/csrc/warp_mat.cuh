@@ -279,6 +279,98 @@ template <int NB, bool SH> __device__ __forceinline__ double cm_redot_partial(co
   return s;
 }
 
+// Conjugation step  P W P'  ( = nt(P, X) with X = nt(conj P, W) = (W P')^T ), the body of the closed-system recursion and of
+// the density-type sweeps.  P is the left operand of both products, so in the three-multiplication form the variant with the
+// operand sums on the LEFT side (K1 = ar (br + bi), K2 = (ai - ar) br, K3 = (ar + ai) bi) needs only s+ = pr + pi and
+// s- = pr - pi for BOTH products (signs flip on the integer pipe): 8 instead of 12 DADD per element pair.
+template <int NB> __device__ __forceinline__ CM<NB> conj_by(const CM<NB>& P, const CM<NB>& W) {
+#if QOC_3M
+  double nsp[NB][NB][2], nsm[NB][NB][2];                      // -(pr + pi),  pi - pr
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int l = 0; l < NB; l++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        nsp[i][l][h] = dneg(P.re[i][l][h] + P.im[i][l][h]);
+        nsm[i][l][h] = P.im[i][l][h] - P.re[i][l][h];
+      }
+  CM<NB> X, R;
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    // pass 0: X = conj(P) W^T  (ai' = -pi: ai' - ar = -s+, ar + ai' = s-);  pass 1: R = P X^T  (ai - ar = -s-, ar + ai = s+)
+    const CM<NB>& B = pass == 0 ? W : X;
+    CM<NB>& C = pass == 0 ? X : R;
+    double sB[NB][NB][2];
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+#pragma unroll
+      for (int l = 0; l < NB; l++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) sB[j][l][h] = B.re[j][l][h] + B.im[j][l][h];
+#pragma unroll
+    for (int i = 0; i < NB; i++)
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        double k0 = 0, k1 = 0;
+#pragma unroll
+        for (int l = 0; l < NB; l++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) dmma(k0, k1, P.re[i][l][h], sB[j][l][h]);                 // K1 = ar (br + bi)
+        double r0 = k0, r1 = k1, m0 = k0, m1 = k1;
+#pragma unroll
+        for (int l = 0; l < NB; l++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            dmma(r0, r1, pass == 0 ? nsm[i][l][h] : nsp[i][l][h], B.im[j][l][h]);               // - K3 = -(ar + ai') bi
+            dmma(m0, m1, pass == 0 ? nsp[i][l][h] : nsm[i][l][h], B.re[j][l][h]);               // + K2 = (ai' - ar) br
+          }
+        C.re[i][j][0] = r0; C.re[i][j][1] = r1; C.im[i][j][0] = m0; C.im[i][j][1] = m1;
+      }
+  }
+  return R;
+#else
+  const CM<NB> X = mul_nt<NB, true, false>(P, W);
+  return mul_nt<NB>(P, X);
+#endif
+}
+// G * G for an anti-Hermitian G, given Gt = G^T = -conj(G): the right operand's sums are the left operand's up to signs
+// (br = -gr, bi = gi: br + bi = gi - gr, bi - br = gr + gi), 4 instead of 6 DADD per element pair.
+template <int NB> __device__ __forceinline__ CM<NB> square_antiherm(const CM<NB>& G) {
+#if QOC_3M
+  double sp[NB][NB][2], dm[NB][NB][2];                        // gr + gi,  gi - gr
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int l = 0; l < NB; l++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) { sp[i][l][h] = G.re[i][l][h] + G.im[i][l][h]; dm[i][l][h] = G.im[i][l][h] - G.re[i][l][h]; }
+  CM<NB> C;
+#pragma unroll
+  for (int i = 0; i < NB; i++)
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      double k0 = 0, k1 = 0;
+#pragma unroll
+      for (int l = 0; l < NB; l++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) dmma(k0, k1, sp[i][l][h], dneg(G.re[j][l][h]));              // K1 = (ar + ai) br,  br = -gr
+      double r0 = k0, r1 = k1, m0 = k0, m1 = k1;
+#pragma unroll
+      for (int l = 0; l < NB; l++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          dmma(r0, r1, dneg(G.im[i][l][h]), dm[j][l][h]);                                       // - K3 = -ai (br + bi)
+          dmma(m0, m1, G.re[i][l][h], sp[j][l][h]);                                             // + K2 = ar (bi - br)
+        }
+      C.re[i][j][0] = r0; C.re[i][j][1] = r1; C.im[i][j][0] = m0; C.im[i][j][1] = m1;
+    }
+  return C;
+#else
+  return mul_nt<NB>(G, cm_negconj<NB>(G));
+#endif
+}
+
 // ---- warp reductions ----------------------------------------------------------------------------------
 template <int GS> __device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
