@@ -41,13 +41,14 @@ __global__ void pack_kernel(const PackParams p) {
 // fixed-order combine).  With a single chunk pass 1 writes the result itself (part == out, no pass 2).
 __global__ void reduce_members_pass1(const double* __restrict__ gradc, const double* __restrict__ fomc,
                                      const double* __restrict__ wts, double* __restrict__ part,
-                                     int M, int NK, int chunk, int nchunks) {
-  // grid: (ceil((NK+1)/256) * R, nchunks); part[r][chunk][NK+1] (entry 0 = fom)
+                                     int M, int NK, int chunk, int nchunks, int ch0) {
+  // grid: (ceil((NK+1)/256) * R, rows of this launch); part[r][chunk][NK+1] (entry 0 = fom); the launch covers the partial
+  // rows ch0 .. ch0 + gridDim.y - 1 (a chain range of the chunk-parallel closed-system mode reduces its own members)
   const int bpr = (NK + 1 + blockDim.x - 1) / blockDim.x;
   int r = blockIdx.x / bpr;
   int e = (blockIdx.x - r * bpr) * blockDim.x + threadIdx.x;
   if (e > NK) return;
-  int ch = blockIdx.y;
+  int ch = ch0 + blockIdx.y;
   int k0 = ch * chunk, k1 = min(M, k0 + chunk);
   double s = 0.0;
   if (e == 0) { for (int k = k0; k < k1; k++) s += wts[k] * fomc[(size_t)r * M + k]; }

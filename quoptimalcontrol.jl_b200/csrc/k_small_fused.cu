@@ -40,9 +40,10 @@ cudaError_t launch_pack(const PackParams& pp, long total, cudaStream_t st) {
   return cudaGetLastError();
 }
 cudaError_t launch_reduce_pass1(const double* gradc, const double* fomc, const double* wts, double* part, int M, int NK, int R,
-                                int chunk, int nchunks, cudaStream_t st) {
-  dim3 g1((unsigned)(((NK + 1 + 255) / 256) * (long)R), nchunks);
-  reduce_members_pass1<<<g1, 256, 0, st>>>(gradc, fomc, wts, part, M, NK, chunk, nchunks);
+                                int chunk, int nchunks, cudaStream_t st, int ch0, int nrows) {
+  if (nrows < 0) nrows = nchunks - ch0;
+  dim3 g1((unsigned)(((NK + 1 + 255) / 256) * (long)R), nrows);
+  reduce_members_pass1<<<g1, 256, 0, st>>>(gradc, fomc, wts, part, M, NK, chunk, nchunks, ch0);
   return cudaGetLastError();
 }
 cudaError_t launch_reduce_pass2(const double* part, double* out, int NK, int R, int nchunks, cudaStream_t st) {

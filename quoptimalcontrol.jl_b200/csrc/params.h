@@ -127,7 +127,7 @@ int closed_persistent_ctl_ints(int n_groups, int Cn);
 // ---- launch wrappers of the non-template kernels (defined in k_small_fused.cu); return cudaGetLastError() ---------------
 cudaError_t launch_pack(const PackParams& pp, long total, cudaStream_t st);
 cudaError_t launch_reduce_pass1(const double* gradc, const double* fomc, const double* wts, double* part, int M, int NK, int R,
-                                int chunk, int nchunks, cudaStream_t st);
+                                int chunk, int nchunks, cudaStream_t st, int ch0 = 0, int nrows = -1);   // partial rows [ch0, ch0 + nrows)
 cudaError_t launch_reduce_pass2(const double* part, double* out, int NK, int R, int nchunks, cudaStream_t st);
 
 }  // namespace qoc
