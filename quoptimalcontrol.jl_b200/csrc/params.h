@@ -96,6 +96,11 @@ struct PhasedParams {
   // bytes (coefficient index 0 = drift, j = control j; 0xff = unused).
   int asm_sparse;
   unsigned asm_lr, asm_li;
+  // sweep_unitary_dmma_item: trace-dots over the union of the controls' non-zero entries only.  dot_tab[0..127] = compact slot
+  // of flat entry f (re plane 0..63, im plane 64..127; -1: no control has a non-zero there), dot_tab[128..255] = flat entry of
+  // slot s (-1: padding); dot_nks = k-steps of 4 slots (a multiple of 4; 0 = dense form, all 32 k-steps).
+  const int* dot_tab;
+  int dot_nks;
   double* fomc;
   double* gradc;
 };

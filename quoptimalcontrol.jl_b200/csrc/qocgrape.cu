@@ -47,6 +47,8 @@ struct qoc_handle {
   int part_lo[MAX_PARTS + 1] = {};       // chain range of every part (later parts smaller: their boundary + sweep stages are the tail)
   cudaStream_t aux[MAX_PARTS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_PARTS] = {};
+  int* dot_tab = nullptr;                // PhasedParams::dot_tab (256 ints), filled by qoc_set_system
+  int dot_nks = 0;
   int asm_sparse = 0;                    // plane-wise generator assembly (PhasedParams::asm_sparse), decided in qoc_set_system
   unsigned asm_lr = 0xffffffffu, asm_li = 0xffffffffu;
   int unitary_fast = 1;                  // closed-system conjugation kernel when the problem is Hermitian (QOC_UNITARY_FAST=0 disables)
@@ -256,6 +258,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
       if (const char* e = getenv("QOC_PERSIST")) h->persist = atoi(e) != 0;
       if (getenv("QOC_ASM_DMMA") && !atoi(getenv("QOC_ASM_DMMA"))) h->persist = 0;      // the A/B switches of the three-launch form
       if (getenv("QOC_DOTS_DMMA") && !atoi(getenv("QOC_DOTS_DMMA"))) h->persist = 0;
+      CR(dev_alloc(h, &h->dot_tab, (size_t)256));
       if (h->persist) {
         int sms = 0;
         CRC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device));
@@ -326,7 +329,7 @@ extern "C" int qoc_destroy(qoc_handle* h) {
   if (h->comm_peers) cudaFree(h->comm_peers);
   if (h->comm_ctl) cudaFree(h->comm_ctl);
   slice_destroy(h);
-  void* bufs[] = {h->persist_ctl, h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
+  void* bufs[] = {h->dot_tab, h->persist_ctl, h->bS, h->bC, h->storeP2, h->stS, h->stC, h->totT, h->totTt, h->tau, h->sys, h->xi, h->xt, h->ident, h->storeP, h->storeS, h->wts, h->x, h->fomc, h->gradc, h->part, h->out, h->staging};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->hx) cudaFreeHost(h->hx);
   if (h->hout) cudaFreeHost(h->hout);
@@ -408,6 +411,34 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
     h->asm_sparse = nr <= 4 && ni <= 4;
     if (const char* e = getenv("QOC_ASM_SPARSE")) h->asm_sparse = h->asm_sparse && atoi(e) != 0;      // A/B testing
     h->asm_lr = lr; h->asm_li = li;
+    // union over controls and members of the non-zero entries of -i dt B_j in the packed layout (flat entry = plane * 64 +
+    // 8 row + col): the trace-dots of the DMMA sweep contract only those (sweep_unitary_dmma_item)
+    h->dot_nks = 0;
+    if (h->dot_tab && d.D <= 8 && d.K >= 1) {
+      bool used[128] = {};
+      for (int k = 0; k < nB; k++)
+        for (int j = 0; j < d.K; j++) {
+          const double* Mx = B + 2 * ((size_t)k * d.K + j) * DD;
+          for (int c = 0; c < d.D; c++)
+            for (int r = 0; r < d.D; r++) {
+              const double* z = Mx + 2 * ((size_t)c * d.D + r);
+              if (z[1] != 0.0) used[8 * r + c] = true;          // real plane of -i dt B = dt Im B
+              if (z[0] != 0.0) used[64 + 8 * r + c] = true;     // imaginary plane = -dt Re B
+            }
+        }
+      int tab[256], n = 0;
+      for (int f = 0; f < 128; f++) tab[f] = used[f] ? n++ : -1;
+      const int nks = ((n + 15) / 16) * 4;                      // four accumulator chains: a multiple of 4 k-steps
+      for (int sidx = 0; sidx < 128; sidx++) tab[128 + sidx] = -1;
+      for (int f = 0; f < 128; f++) if (tab[f] >= 0) tab[128 + tab[f]] = f;
+      bool sparse_dots = n > 0 && nks <= 24;                    // at least a quarter of the 32 dense k-steps saved
+      if (const char* e = getenv("QOC_DOTS_SPARSE")) sparse_dots = sparse_dots && atoi(e) != 0;      // A/B testing
+      if (sparse_dots) {
+        QOC_CUDA(h, cudaMemcpyAsync(h->dot_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
+        QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->dot_nks = nks;
+      }
+    }
   }
   auto upload = [&](const double* src, size_t count) -> int {
     QOC_CUDA(h, cudaMemcpyAsync(h->staging, src, count * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
@@ -506,6 +537,7 @@ static PhasedParams phased_params(qoc_handle* h, const double* x_dev) {
   p.totT = h->totT; p.totTt = h->totTt; p.tau = h->tau; p.fomc = h->fomc; p.gradc = h->gradc;
   p.bS = h->bS; p.bC = h->bC; p.sys_in_smem = 0; p.store_plain = 0;
   p.asm_sparse = h->asm_sparse; p.asm_lr = h->asm_lr; p.asm_li = h->asm_li;
+  p.dot_tab = h->dot_tab; p.dot_nks = h->dot_nks;
   p.w_off = 0; p.w_cnt = h->n_groups;
   return p;
 }

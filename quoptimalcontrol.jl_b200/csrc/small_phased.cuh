@@ -446,11 +446,25 @@ __device__ __forceinline__ void sweep_unitary_dmma_item(const PhasedParams& p, d
   const Lane L(threadIdx.x & 31);
   const Slot<1> sl(p.pack_mode, p.n_inner, p.M, p.R, L, w);
   const int N = p.N, K = p.K;
+  const int nks = p.dot_nks;                                  // > 0: only the union of the controls' non-zero entries is contracted
+  int o_r0 = 0, o_r1 = 0, o_i0 = 0, o_i1 = 0;                 // compact slots of this lane's four W values (-1: not needed)
   {
     const double* Bm = reinterpret_cast<const double*>(p.sys + (size_t)sl.sysgroup * p.nmat * E + E);
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-      const int ks = i >> 5, ln = i & 31, cc = ln >> 2, q = ln & 3;
-      Bd[i] = cc < K ? Bm[(size_t)cc * (2 * E) + 4 * ks + q] : 0.0;
+    if (nks) {
+      for (int i = threadIdx.x; i < nks * 32; i += blockDim.x) {
+        const int ks = i >> 5, ln = i & 31, cc = ln >> 2, q = ln & 3;
+        const int f = __ldg(p.dot_tab + 128 + 4 * ks + q);
+        Bd[i] = (cc < K && f >= 0) ? Bm[(size_t)cc * (2 * E) + f] : 0.0;
+      }
+      o_r0 = __ldg(p.dot_tab + 2 * L.lane); o_r1 = __ldg(p.dot_tab + 2 * L.lane + 1);
+      o_i0 = __ldg(p.dot_tab + 64 + 2 * L.lane); o_i1 = __ldg(p.dot_tab + 64 + 2 * L.lane + 1);
+      for (int r = 0; r < 8; r++)                             // padding slots are never stored to: they must hold finite values
+        for (int sidx = L.lane; sidx < 4 * nks; sidx += 32) Wb[r * DOT_LD + sidx] = 0.0;
+    } else {
+      for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        const int ks = i >> 5, ln = i & 31, cc = ln >> 2, q = ln & 3;
+        Bd[i] = cc < K ? Bm[(size_t)cc * (2 * E) + 4 * ks + q] : 0.0;
+      }
     }
   }
   __syncthreads();
@@ -467,21 +481,38 @@ __device__ __forceinline__ void sweep_unitary_dmma_item(const PhasedParams& p, d
       const int t = tb + i;
       const CM<NB> P = Pn;
       if (t + 1 < t1) Pn = cm_load<NB>(L, stP + (size_t)(t + 1) * E);
-      double* row = Wb + i * DOT_LD + 2 * L.lane;
-      *reinterpret_cast<double2*>(row) = make_double2(W.re[0][0][0], W.re[0][0][1]);
-      *reinterpret_cast<double2*>(row + 64) = make_double2(W.im[0][0][0], W.im[0][0][1]);
+      if (nks) {
+        double* row = Wb + i * DOT_LD;
+        if (o_r0 >= 0) row[o_r0] = W.re[0][0][0];
+        if (o_r1 >= 0) row[o_r1] = W.re[0][0][1];
+        if (o_i0 >= 0) row[o_i0] = W.im[0][0][0];
+        if (o_i1 >= 0) row[o_i1] = W.im[0][0][1];
+      } else {
+        double* row = Wb + i * DOT_LD + 2 * L.lane;
+        *reinterpret_cast<double2*>(row) = make_double2(W.re[0][0][0], W.re[0][0][1]);
+        *reinterpret_cast<double2*>(row + 64) = make_double2(W.im[0][0][0], W.im[0][0][1]);
+      }
       if (t + 1 < t1) W = conj_by<NB>(P, W);
     }
     __syncwarp();
     double a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0;      // four accumulator chains
     const double* bp = Bd + L.lane;
     const double* wp = Wb + L.g * DOT_LD + L.q;
+    if (nks) {
+      for (int ks = 0; ks < nks; ks += 4) {
+        dmma(a0, a1, bp[(ks + 0) * 32], wp[4 * (ks + 0)]);
+        dmma(b0, b1, bp[(ks + 1) * 32], wp[4 * (ks + 1)]);
+        dmma(c0, c1, bp[(ks + 2) * 32], wp[4 * (ks + 2)]);
+        dmma(d0, d1, bp[(ks + 3) * 32], wp[4 * (ks + 3)]);
+      }
+    } else {
 #pragma unroll
-    for (int ks = 0; ks < 32; ks += 4) {
-      dmma(a0, a1, bp[(ks + 0) * 32], wp[4 * (ks + 0)]);
-      dmma(b0, b1, bp[(ks + 1) * 32], wp[4 * (ks + 1)]);
-      dmma(c0, c1, bp[(ks + 2) * 32], wp[4 * (ks + 2)]);
-      dmma(d0, d1, bp[(ks + 3) * 32], wp[4 * (ks + 3)]);
+      for (int ks = 0; ks < 32; ks += 4) {
+        dmma(a0, a1, bp[(ks + 0) * 32], wp[4 * (ks + 0)]);
+        dmma(b0, b1, bp[(ks + 1) * 32], wp[4 * (ks + 1)]);
+        dmma(c0, c1, bp[(ks + 2) * 32], wp[4 * (ks + 2)]);
+        dmma(d0, d1, bp[(ks + 3) * 32], wp[4 * (ks + 3)]);
+      }
     }
     const double g0 = (a0 + b0) + (c0 + d0), g1 = (a1 + b1) + (c1 + d1);
     if (cc < K && sl.valid) {
