@@ -101,6 +101,11 @@ struct PhasedParams {
   // slot s (-1: padding); dot_nks = k-steps of 4 slots (a multiple of 4; 0 = dense form, all 32 k-steps).
   const int* dot_tab;
   int dot_nks;
+  // plane-wise assembly over the union of the matrices' non-zero entries only: asm_pos[8 b + g] = flat entry (row g of compact
+  // block b; -1 = padding), blocks [0, asm_nblk_re) belong to the real plane, [asm_nblk_re, asm_nblk) to the imaginary plane;
+  // asm_nblk = 0: all 16 blocks in natural order.  Entries outside the union are zero in every generator.
+  const int* asm_pos;
+  int asm_nblk_re, asm_nblk;
   double* fomc;
   double* gradc;
 };

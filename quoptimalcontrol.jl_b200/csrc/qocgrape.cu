@@ -47,8 +47,9 @@ struct qoc_handle {
   int part_lo[MAX_PARTS + 1] = {};       // chain range of every part (later parts smaller: their boundary + sweep stages are the tail)
   cudaStream_t aux[MAX_PARTS] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_PARTS] = {};
-  int* dot_tab = nullptr;                // PhasedParams::dot_tab (256 ints), filled by qoc_set_system
+  int* dot_tab = nullptr;                // PhasedParams::dot_tab (256 ints) + asm_pos (128 ints), filled by qoc_set_system
   int dot_nks = 0;
+  int asm_nblk = 0, asm_nblk_re = 0;
   int asm_sparse = 0;                    // plane-wise generator assembly (PhasedParams::asm_sparse), decided in qoc_set_system
   unsigned asm_lr = 0xffffffffu, asm_li = 0xffffffffu;
   int unitary_fast = 1;                  // closed-system conjugation kernel when the problem is Hermitian (QOC_UNITARY_FAST=0 disables)
@@ -258,7 +259,7 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
       if (const char* e = getenv("QOC_PERSIST")) h->persist = atoi(e) != 0;
       if (getenv("QOC_ASM_DMMA") && !atoi(getenv("QOC_ASM_DMMA"))) h->persist = 0;      // the A/B switches of the three-launch form
       if (getenv("QOC_DOTS_DMMA") && !atoi(getenv("QOC_DOTS_DMMA"))) h->persist = 0;
-      CR(dev_alloc(h, &h->dot_tab, (size_t)256));
+      CR(dev_alloc(h, &h->dot_tab, (size_t)384));
       if (h->persist) {
         int sms = 0;
         CRC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device));
@@ -413,6 +414,38 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
     h->asm_lr = lr; h->asm_li = li;
     // union over controls and members of the non-zero entries of -i dt B_j in the packed layout (flat entry = plane * 64 +
     // 8 row + col): the trace-dots of the DMMA sweep contract only those (sweep_unitary_dmma_item)
+    // union over all matrices and members of the non-zero generator entries, per plane, in compact blocks of 8
+    h->asm_nblk = h->asm_nblk_re = 0;
+    if (h->dot_tab && d.D <= 8 && h->asm_sparse) {
+      bool used[128] = {};
+      for (int j = 0; j <= d.K; j++) {
+        const int nsrc = j == 0 ? nA : nB;
+        for (int k = 0; k < nsrc; k++) {
+          const double* Mx = j == 0 ? A + 2 * (size_t)k * DD : B + 2 * ((size_t)k * d.K + (j - 1)) * DD;
+          for (int c = 0; c < d.D; c++)
+            for (int r = 0; r < d.D; r++) {
+              const double* z = Mx + 2 * ((size_t)c * d.D + r);
+              if (z[1] != 0.0) used[8 * r + c] = true;
+              if (z[0] != 0.0) used[64 + 8 * r + c] = true;
+            }
+        }
+      }
+      int pos[128], n = 0, nre = 0;
+      for (int pl = 0; pl < 2; pl++) {
+        for (int f = 64 * pl; f < 64 * pl + 64; f++) if (used[f]) pos[n++] = f;
+        while (n % 8) pos[n++] = -1;
+        if (pl == 0) nre = n / 8;
+      }
+      const int nblk = n / 8;
+      for (int i = n; i < 128; i++) pos[i] = -1;
+      bool compact = nblk > 0 && nblk <= 12;                    // at least a quarter of the 16 natural blocks saved
+      if (const char* e = getenv("QOC_ASM_COMPACT")) compact = compact && atoi(e) != 0;      // A/B testing
+      if (compact) {
+        QOC_CUDA(h, cudaMemcpyAsync(h->dot_tab + 256, pos, sizeof(pos), cudaMemcpyHostToDevice, h->stream));
+        QOC_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->asm_nblk = nblk; h->asm_nblk_re = nre;
+      }
+    }
     h->dot_nks = 0;
     if (h->dot_tab && d.D <= 8 && d.K >= 1) {
       bool used[128] = {};
@@ -538,6 +571,7 @@ static PhasedParams phased_params(qoc_handle* h, const double* x_dev) {
   p.bS = h->bS; p.bC = h->bC; p.sys_in_smem = 0; p.store_plain = 0;
   p.asm_sparse = h->asm_sparse; p.asm_lr = h->asm_lr; p.asm_li = h->asm_li;
   p.dot_tab = h->dot_tab; p.dot_nks = h->dot_nks;
+  p.asm_pos = h->dot_tab ? h->dot_tab + 256 : nullptr; p.asm_nblk = h->asm_nblk; p.asm_nblk_re = h->asm_nblk_re;
   p.w_off = 0; p.w_cnt = h->n_groups;
   return p;
 }

@@ -554,7 +554,17 @@ __device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, doub
   const int jr = (int)((p.asm_lr >> (8 * L.q)) & 0xffu), ji = (int)((p.asm_li >> (8 * L.q)) & 0xffu);   // this lane's k index -> coefficient
   {
     const double* sysd = reinterpret_cast<const double*>(p.sys + (size_t)sl.sysgroup * p.nmat * E);
-    if (sparse) {       // Ad [16 m-blocks][32 lanes]: blocks 0..7 = real plane (list asm_lr), 8..15 = imaginary plane (asm_li)
+    if (sparse && p.asm_nblk) {    // compact blocks over the union of non-zero entries; position table behind the coefficients
+      int* posS = reinterpret_cast<int*>(Ad + 512);
+      for (int i = threadIdx.x; i < p.asm_nblk * 32; i += blockDim.x) {
+        const int ln = i & 31, b = i >> 5, g = ln >> 2, q = ln & 3;
+        const int f = __ldg(p.asm_pos + 8 * b + g);
+        const int j = (int)(((b < p.asm_nblk_re ? p.asm_lr : p.asm_li) >> (8 * q)) & 0xffu);
+        Ad[i] = (f >= 0 && j <= K) ? sysd[(size_t)j * (2 * E) + f] : 0.0;
+      }
+      for (int i = threadIdx.x; i < 128; i += blockDim.x) posS[i] = i < 8 * p.asm_nblk ? __ldg(p.asm_pos + i) : -1;
+      for (int i = L.lane; i < 8 * DOT_LD; i += 32) Gb[i] = 0.0;      // entries outside the union stay zero in rows 1..7
+    } else if (sparse) {       // Ad [16 m-blocks][32 lanes]: blocks 0..7 = real plane (list asm_lr), 8..15 = imaginary plane (asm_li)
       for (int i = threadIdx.x; i < 512; i += blockDim.x) {
         const int ln = i & 31, mb = i >> 5, g = ln >> 2, q = ln & 3;
         const int j = (int)(((mb < 8 ? p.asm_lr : p.asm_li) >> (8 * q)) & 0xffu);
@@ -601,7 +611,21 @@ __device__ __forceinline__ void chunk_expm_dmma_item(const PhasedParams& p, doub
 #endif
       const double* ap = Ad + L.lane;
       double* gp = Gb + (2 * L.q) * DOT_LD + L.g;
-      if (sparse) {
+      if (sparse && p.asm_nblk) {
+        // row 0 doubles as the transpose tile: clear it again, then scatter the blocks' results to their flat positions
+        *reinterpret_cast<double2*>(Gb + 2 * L.lane) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(Gb + 64 + 2 * L.lane) = make_double2(0.0, 0.0);
+        __syncwarp();
+        const int* posS = reinterpret_cast<const int*>(Ad + 512) + L.g;
+        double* gq = Gb + (2 * L.q) * DOT_LD;
+        const int nblk = p.asm_nblk, nre = p.asm_nblk_re;
+        for (int b = 0; b < nblk; b++) {
+          double d0 = 0.0, d1 = 0.0;
+          dmma(d0, d1, ap[b * 32], b < nre ? b0 : b1);
+          const int f = posS[8 * b];
+          if (f >= 0) { gq[f] = d0; gq[f + DOT_LD] = d1; }
+        }
+      } else if (sparse) {
 #pragma unroll
         for (int mb = 0; mb < 16; mb++) {
           double d0 = 0.0, d1 = 0.0;

@@ -1,6 +1,6 @@
 """GPU parity of the structure-dependent forms of the D = 5..8 closed-system kernels against the oracle: the plane-wise DMMA
-generator assembly (at most 4 matrices with a real plane, 4 with an imaginary plane) and the trace-dots over the union of the
-controls' non-zero entries.  Both are decided in qoc_set_system from the matrices of ALL members; the cases below flip every
+generator assembly (at most 4 matrices with a real plane, 4 with an imaginary plane; natural blocks or compact blocks over the
+union of the non-zero entries) and the trace-dots over the union of the controls' non-zero entries.  Both are decided in qoc_set_system from the matrices of ALL members; the cases below flip every
 decision (and the environment switches force the dense forms on the same inputs).  Chain counts are chosen so that the
 chunk-parallel closed-system kernels run (>= 150 chains, N >= 64)."""
 import os
@@ -67,7 +67,7 @@ def _members(kind, D, M, seed):
 
 @pytest.mark.parametrize("kind,D", [("pauli", 8), ("pauli_k7", 8), ("real_sparse", 8), ("real_sparse", 6), ("mixed_member", 5),
                                     ("dense", 8), ("dense", 7)])
-@pytest.mark.parametrize("env", [{}, {"QOC_ASM_SPARSE": "0", "QOC_DOTS_SPARSE": "0"}, {"QOC_PERSIST": "1"}])
+@pytest.mark.parametrize("env", [{}, {"QOC_ASM_COMPACT": "0"}, {"QOC_ASM_SPARSE": "0", "QOC_DOTS_SPARSE": "0"}, {"QOC_PERSIST": "1"}])
 def test_structure_dependent_closed_kernels(monkeypatch, kind, D, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
