@@ -1,0 +1,152 @@
+"""CPU checks (numpy) of the algebra behind the round-2 kernel forms.  Each test restates the exact operation sequence of the
+device code it cites and compares it with the plain formula, so an error in the derivation cannot hide behind the GPU tests'
+tolerances.  No GPU needed."""
+import math
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+RNG = np.random.default_rng(20261017)
+
+# constants of csrc/small_d.cuh (Bader, Blanes, Casas 2019) and their recombination (T8_YA .. T8_R7)
+X1, X2, X3, X4 = 0.10836465678522780852, 0.027091164196306952131, 2.0 / 3.0, 0.54676145797072405251
+X5, X6, X7, Y2 = 0.16112557339541759283, 0.014090917158378207731, 0.033792797010870504141, 0.13549236135285063166
+YA, YB = 0.25, 6.1520673478250353627
+R4, R5, R6, R7 = 0.059249617736388271447, 0.017460317460317460317, -0.00091433916494050425595, 0.00039682539682539682538
+
+
+def _antiherm(D, norm1):
+    H = RNG.standard_normal((D, D)) + 1j * RNG.standard_normal((D, D))
+    G = -1j * (H + H.conj().T)
+    return G * (norm1 / np.linalg.norm(G, 1))
+
+
+def test_recombined_taylor8_equals_the_three_product_scheme_and_exp():
+    """expm_t8 (csrc/small_d.cuh): Yh = A + YA A2 + YB I, Lh = A2 Yh, Rh = R4 I + R5 A + R6 A2 + R7 Lh, T8 = I + A + Y2 A2 + Lh Rh
+    is the same polynomial as A4 = A2 (x1 A + x2 A2), A8 = (x3 A2 + A4)(x4 I + x5 A + x6 A2 + x7 A4), T8 = I + A + y2 A2 + A8,
+    and both equal sum_k A^k / k!, k <= 8; at the scaling threshold 0.0694 that is exp(A) to double precision."""
+    assert abs(YA - X2 / X1) < 1e-17 and abs(YB - X3 / X1) < 1e-15
+    assert abs(R4 - X1 * X4) < 1e-17 and abs(R5 - X1 * X5) < 1e-17 and abs(R5 - 11 / 630) < 1e-17
+    assert abs(R6 - X1 * (X6 - X7 * X3)) < 1e-18 and abs(R7 - X1 * X1 * X7) < 1e-18 and abs(R7 - 1 / 2520) < 1e-18
+    for D in (3, 8, 16):
+        A = _antiherm(D, 0.0694)
+        I = np.eye(D)
+        A2 = A @ A
+        A4 = A2 @ (X1 * A + X2 * A2)
+        T8_ref = I + A + Y2 * A2 + (X3 * A2 + A4) @ (X4 * I + X5 * A + X6 * A2 + X7 * A4)
+        Lh = A2 @ (A + YA * A2 + YB * I)
+        T8_new = I + A + Y2 * A2 + Lh @ (R4 * I + R5 * A + R6 * A2 + R7 * Lh)
+        series = sum(np.linalg.matrix_power(A, k) / float(math.factorial(k)) for k in range(9))
+        assert np.max(np.abs(T8_new - T8_ref)) < 5e-16
+        assert np.max(np.abs(T8_new - series)) < 5e-16
+        assert np.max(np.abs(T8_new - scipy.linalg.expm(A))) < 1e-15
+
+
+def _nt_3m(a, b, conj_a=False, conj_b=False, acc=None):
+    """mul_nt_impl with QOC_3M (csrc/warp_mat.cuh): C (+)= op(A) op(B)^T through K1 = (ar + ai') br, K3 = ai' (br + bi'),
+    K2 = ar (bi' - br); K1 seeds both accumulators."""
+    ar, ai = a.real, (-a.imag if conj_a else a.imag)
+    br, bi = b.real, (-b.imag if conj_b else b.imag)
+    sA, sB, dB = ar + ai, br + bi, bi - br
+    k = sA @ br.T + (acc.real if acc is not None else 0.0)
+    re = k + (-ai) @ sB.T
+    m0 = k + ((acc.imag - acc.real) if acc is not None else 0.0)
+    im = m0 + ar @ dB.T
+    return re + 1j * im
+
+
+@pytest.mark.parametrize("conj_a,conj_b", [(False, False), (True, False), (False, True), (True, True)])
+def test_three_multiplication_product_all_conjugation_variants(conj_a, conj_b):
+    for D in (8, 16):
+        a = RNG.standard_normal((D, D)) + 1j * RNG.standard_normal((D, D))
+        b = RNG.standard_normal((D, D)) + 1j * RNG.standard_normal((D, D))
+        c = RNG.standard_normal((D, D)) + 1j * RNG.standard_normal((D, D))
+        ref = (a.conj() if conj_a else a) @ (b.conj() if conj_b else b).T
+        assert np.max(np.abs(_nt_3m(a, b, conj_a, conj_b) - ref)) < 1e-13 * D
+        assert np.max(np.abs(_nt_3m(a, b, conj_a, conj_b, acc=c) - (c + ref))) < 1e-13 * D
+
+
+def test_conjugation_step_with_left_operand_sums():
+    """conj_by (csrc/warp_mat.cuh): X = conj(P) W^T and R = P X^T = P W P' with K1 = ar (br + bi), K2 = (ai' - ar) br,
+    K3 = (ar + ai') bi; both passes use only -(pr + pi) and pi - pr of P."""
+    for D in (8, 16):
+        P = scipy.linalg.expm(_antiherm(D, 0.7))
+        W = RNG.standard_normal((D, D)) + 1j * RNG.standard_normal((D, D))
+        pr, pi = P.real, P.imag
+        nsp, nsm = -(pr + pi), pi - pr
+        out = []
+        B = W
+        for first in (True, False):
+            sB = B.real + B.imag
+            k = pr @ sB.T
+            re = k + (nsm if first else nsp) @ B.imag.T
+            im = k + (nsp if first else nsm) @ B.real.T
+            B = re + 1j * im
+            out.append(B)
+        assert np.max(np.abs(out[0] - P.conj() @ W.T)) < 1e-13 * D
+        assert np.max(np.abs(out[1] - P @ W @ P.conj().T)) < 1e-13 * D
+
+
+def test_square_of_an_antihermitian_generator_shares_its_sums():
+    """square_antiherm (csrc/warp_mat.cuh): G G = nt(G, Gt), Gt = G^T = -conj(G); with br = -gr, bi = gi the right operand's sums
+    are gi - gr and gr + gi, the latter being the left operand's own."""
+    for D in (8, 16):
+        G = _antiherm(D, 0.05)
+        gr, gi = G.real, G.imag
+        sp, dm = gr + gi, gi - gr
+        k = sp @ (-gr).T
+        re = k + (-gi) @ dm.T
+        im = k + gr @ sp.T
+        assert np.max(np.abs((re + 1j * im) - G @ G)) < 1e-17 * D
+        assert np.max(np.abs(G.T + G.conj())) == 0.0
+
+
+def test_infinity_norm_serves_the_taylor_bound():
+    """cm_norm1_bound with QOC_NORM_INF: row sums of |re| + |im| bound the induced infinity norm from above (|z| <= |re| + |im|),
+    and the degree-8 truncation error at that bound stays below 2^-53 like for the 1-norm."""
+    for D in (5, 8, 16):
+        G = _antiherm(D, 1.0)
+        bound = np.max(np.sum(np.abs(G.real) + np.abs(G.imag), axis=1))
+        assert bound >= np.linalg.norm(G, np.inf)
+        s = max(0, int(np.floor(np.log2(bound / 0.0694))) + 1) if bound > 0.0694 else 0
+        A = G / 2.0 ** s
+        assert np.linalg.norm(A, np.inf) <= 0.0694 * 1.0000001
+        T8 = sum(np.linalg.matrix_power(A, k) / float(math.factorial(k)) for k in range(9))
+        assert np.max(np.abs(T8 - scipy.linalg.expm(A))) < 2e-16 * D
+
+
+def _tables(members, D, K):
+    """numpy restatement of the structure analysis in qoc_set_system (csrc/qocgrape.cu): plane lists, compact assembly blocks,
+    compact dot slots.  Flat entry of the packed layout: plane * 64 + 8 row + col; the packed matrices are -i dt X, so their
+    real plane is dt Im X and their imaginary plane -dt Re X."""
+    mats = [[m[0] for m in members]] + [[m[1][j] for m in members] for j in range(K)]
+    lr = [j for j, ms in enumerate(mats) if any(np.any(x.imag != 0) for x in ms)]
+    li = [j for j, ms in enumerate(mats) if any(np.any(x.real != 0) for x in ms)]
+    used = np.zeros(128, bool)
+    used_b = np.zeros(128, bool)
+    for j, ms in enumerate(mats):
+        for x in ms:
+            for r in range(D):
+                for c in range(D):
+                    if x[r, c].imag != 0:
+                        used[8 * r + c] = True
+                        used_b[8 * r + c] |= j > 0
+                    if x[r, c].real != 0:
+                        used[64 + 8 * r + c] = True
+                        used_b[64 + 8 * r + c] |= j > 0
+    nblk_re = -(-int(used[:64].sum()) // 8)
+    nblk = nblk_re + -(-int(used[64:].sum()) // 8)
+    nks = -(-int(used_b.sum()) // 16) * 4
+    return lr, li, nblk_re, nblk, nks
+
+
+def test_structure_tables_of_the_bench_config():
+    """cfg4 (the bench default): 3 matrices with a real plane (sigma_y controls), 4 with an imaginary plane (diagonal drift,
+    sigma_x controls) -> plane-wise assembly; 24 + 32 non-zero generator entries -> 3 + 4 compact blocks instead of 16;
+    48 non-zero control entries -> 12 dot k-steps instead of 32.  These are the counts DESIGN.md section 3.2 quotes."""
+    import quoptimalcontrol_jl_b200 as qoc
+    cfg = qoc.configs.config4(N=4, grid=3)
+    lr, li, nblk_re, nblk, nks = _tables(cfg["members"], 8, 6)
+    assert lr == [2, 4, 6] and li == [0, 1, 3, 5]
+    assert (nblk_re, nblk, nks) == (3, 7, 12)
