@@ -210,6 +210,14 @@ typedef struct qoc_lbfgs_result {
 int qoc_minimize_lbfgs(qoc_handle* h, const double* x0, const qoc_lbfgs_options* opt, double* x_out, qoc_lbfgs_result* res);
 
 int qoc_get_stats(qoc_handle* h, qoc_stats* out);
+/* Diagnostics (pure host code, no CUDA call, usable without a GPU): the exact elementwise structure qoc_set_system derives
+   from the caller's matrices to select kernel forms -- Hermiticity (closed-system recursion; the reference has no such
+   notion: /root/reference/src/GRAPE.jl:53-75 always runs the general sweeps), which of -i dt A, -i dt B_j have a real /
+   imaginary plane, and the unions of non-zero entries for the compact generator assembly and the compact trace-dots
+   (D <= 8).  A [M or 1][D*D], B [M or 1][K][D*D] as in qoc_set_system.
+   out (392 ints): [0] herm, [1] asm_sparse, [2] asm_lr, [3] asm_li (4 packed bytes each: 0 = drift, j = control j, 0xff =
+   unused), [4] asm_nblk_re, [5] asm_nblk, [6] dot_nks, [7] 0, [8..135] asm_pos, [136..391] dot_tab. */
+int qoc_analyze_structure(int D, int K, int M, const double* A, const double* B, int shared_flags, int* out);
 /* Message of the last error on this handle (or of the last failed qoc_create when h == NULL). */
 const char* qoc_last_error(qoc_handle* h);
 

@@ -18,7 +18,7 @@ EXPORTS = ["qoc_version", "qoc_create", "qoc_destroy", "qoc_set_system", "qoc_ev
            "qoc_total_propagator", "qoc_propagators", "qoc_get_stats", "qoc_last_error",
            "qoc_comm_export", "qoc_comm_connect", "qoc_eval_allreduce_device", "qoc_minimize_lbfgs",
            "qoc_set_states", "qoc_eval_continue", "qoc_eval_allreduce", "qoc_set_penalty",
-           "qoc_slice_export", "qoc_slice_connect", "qoc_eval_slice"]
+           "qoc_slice_export", "qoc_slice_connect", "qoc_eval_slice", "qoc_analyze_structure"]
 
 
 class QocDesc(C.Structure):

@@ -357,6 +357,95 @@ static int pack_one(qoc_handle* h, const double2* src_dev, int n_src, long src_s
   return launch_check(h, "pack_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------ structure of a system
+// Exact (elementwise) properties of the caller's matrices that select kernel forms; pure host code, also reachable through
+// qoc_analyze_structure for CPU-side tests.  A [nA][D*D], B [nB][K][D*D], column-major complex.  The kernels work on the
+// scaled matrices -i dt X in the packed layout (flat entry = plane * 64 + 8 row + col for D <= 8): their real plane is
+// dt Im X, their imaginary plane -dt Re X.
+struct SystemStructure {
+  int herm;                    // drift and all controls Hermitian  =>  anti-Hermitian generators, unitary propagators
+  int asm_sparse;              // at most 4 of the 1 + K matrices have a real plane and at most 4 an imaginary plane (any member)
+  unsigned asm_lr, asm_li;     // those matrices as 4 packed bytes (0 = drift, j = control j, 0xff = unused)
+  int asm_nblk_re, asm_nblk;   // D <= 8: compact assembly blocks of 8 over the union of non-zero generator entries
+                               // (real-plane blocks first); asm_nblk = 0 when fewer than a quarter of the 16 natural blocks is saved
+  int dot_nks;                 // D <= 8: k-steps of the trace-dots over the union of the controls' non-zero entries (a multiple
+                               // of 4); 0 when fewer than a quarter of the 32 dense k-steps is saved
+  int asm_pos[128];            // flat entry of row g of block b at [8 b + g], -1 = padding
+  int dot_tab[256];            // [f] = compact slot of flat entry f or -1;  [128 + s] = flat entry of slot s or -1
+};
+static void analyze_structure(int D, int K, int nA, int nB, const double* A, const double* B, SystemStructure& s) {
+  const size_t DD = (size_t)D * D;
+  auto mat = [&](int j, int k) { return j == 0 ? A + 2 * (size_t)k * DD : B + 2 * ((size_t)k * K + (j - 1)) * DD; };
+  auto is_herm = [&](const double* Mx) {
+    for (int c = 0; c < D; c++)
+      for (int r = 0; r <= c; r++) {
+        const double* a = Mx + 2 * ((size_t)c * D + r); const double* b = Mx + 2 * ((size_t)r * D + c);
+        if (a[0] != b[0] || a[1] != -b[1]) return false;
+      }
+    return true;
+  };
+  bool herm = true;
+  for (int j = 0; j <= K && herm; j++)
+    for (int k = 0; k < (j == 0 ? nA : nB) && herm; k++) herm = is_herm(mat(j, k));
+  s.herm = herm ? 1 : 0;
+  // plane lists of the plane-wise DMMA assembly
+  s.asm_lr = s.asm_li = 0xffffffffu;
+  int nr = 0, ni = 0;
+  for (int j = 0; j <= K; j++) {
+    bool any_re = false, any_im = false;
+    for (int k = 0; k < (j == 0 ? nA : nB); k++) {
+      const double* Mx = mat(j, k);
+      for (size_t e = 0; e < DD; e++) { any_re = any_re || Mx[2 * e] != 0.0; any_im = any_im || Mx[2 * e + 1] != 0.0; }
+    }
+    if (any_im) { if (nr < 4) s.asm_lr = (s.asm_lr & ~(0xffu << (8 * nr))) | ((unsigned)j << (8 * nr)); nr++; }
+    if (any_re) { if (ni < 4) s.asm_li = (s.asm_li & ~(0xffu << (8 * ni))) | ((unsigned)j << (8 * ni)); ni++; }
+  }
+  s.asm_sparse = nr <= 4 && ni <= 4;
+  s.asm_nblk = s.asm_nblk_re = s.dot_nks = 0;
+  for (int& v : s.asm_pos) v = -1;
+  for (int& v : s.dot_tab) v = -1;
+  if (D > 8) return;
+  // non-zero entries of the scaled matrices in the packed layout: all matrices (generator), controls only (trace-dots)
+  bool used_all[128] = {}, used_ctl[128] = {};
+  for (int j = 0; j <= K; j++)
+    for (int k = 0; k < (j == 0 ? nA : nB); k++) {
+      const double* Mx = mat(j, k);
+      for (int c = 0; c < D; c++)
+        for (int r = 0; r < D; r++) {
+          const double* z = Mx + 2 * ((size_t)c * D + r);
+          if (z[1] != 0.0) { used_all[8 * r + c] = true; if (j > 0) used_ctl[8 * r + c] = true; }
+          if (z[0] != 0.0) { used_all[64 + 8 * r + c] = true; if (j > 0) used_ctl[64 + 8 * r + c] = true; }
+        }
+    }
+  {  // compact assembly blocks
+    int n = 0, nre = 0;
+    for (int pl = 0; pl < 2; pl++) {
+      for (int f = 64 * pl; f < 64 * pl + 64; f++) if (used_all[f]) s.asm_pos[n++] = f;
+      while (n % 8) s.asm_pos[n++] = -1;
+      if (pl == 0) nre = n / 8;
+    }
+    if (n > 0 && n / 8 <= 12) { s.asm_nblk = n / 8; s.asm_nblk_re = nre; }
+  }
+  {  // compact trace-dot slots
+    int n = 0;
+    for (int f = 0; f < 128; f++) if (used_ctl[f]) { s.dot_tab[f] = n; s.dot_tab[128 + n] = f; n++; }
+    const int nks = ((n + 15) / 16) * 4;                        // four accumulator chains: a multiple of 4 k-steps
+    if (n > 0 && nks <= 24) s.dot_nks = nks;
+  }
+}
+// out: [0] herm, [1] asm_sparse, [2] asm_lr, [3] asm_li, [4] asm_nblk_re, [5] asm_nblk, [6] dot_nks, [7] 0,
+//      [8 .. 135] asm_pos, [136 .. 391] dot_tab   (392 ints).  No CUDA call: usable without a GPU.
+extern "C" int qoc_analyze_structure(int D, int K, int M, const double* A, const double* B, int shared_flags, int* out) {
+  if (D < 1 || K < 0 || M < 1 || !A || (K > 0 && !B) || !out) return QOC_EINVAL;
+  SystemStructure s;
+  analyze_structure(D, K, (shared_flags & QOC_SHARED_A) ? 1 : M, (shared_flags & QOC_SHARED_B) ? 1 : M, A, B, s);
+  out[0] = s.herm; out[1] = s.asm_sparse; out[2] = (int)s.asm_lr; out[3] = (int)s.asm_li;
+  out[4] = s.asm_nblk_re; out[5] = s.asm_nblk; out[6] = s.dot_nks; out[7] = 0;
+  memcpy(out + 8, s.asm_pos, sizeof(s.asm_pos));
+  memcpy(out + 136, s.dot_tab, sizeof(s.dot_tab));
+  return QOC_OK;
+}
+
 extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, const double* Xi, const double* Xt,
                               const double* wts, int shared_flags) {
   if (!h) return QOC_EINVAL;
@@ -381,96 +470,26 @@ extern "C" int qoc_set_system(qoc_handle* h, const double* A, const double* B, c
   const int member_mode = h->pack_mode;   // 0: slot -> member og*CPW+s ; 1: all slots -> member og
   const double dt = d.T / d.N;              // A, B are packed pre-multiplied by -i*dt
   const int tr_states = d.sys_type == QOC_UNITARY_GATE ? 1 : 0;   // the unitary chain runs on S^T, C^T
-  {  // Hermitian drift and controls  =>  anti-Hermitian generators (exact elementwise test)
-    auto is_herm = [&](const double* Mx) {
-      for (int c = 0; c < d.D; c++)
-        for (int r = 0; r <= c; r++) {
-          const double* a = Mx + 2 * ((size_t)c * d.D + r); const double* b = Mx + 2 * ((size_t)r * d.D + c);
-          if (a[0] != b[0] || a[1] != -b[1]) return false;
-        }
-      return true;
-    };
-    bool herm = true;
+  {  // exact, elementwise structure of the caller's matrices (analyze_structure): which kernel forms apply
     const int nA = (shared_flags & QOC_SHARED_A) ? 1 : d.M, nB = (shared_flags & QOC_SHARED_B) ? 1 : d.M;
-    for (int k = 0; k < nA && herm; k++) herm = is_herm(A + 2 * (size_t)k * DD);
-    for (int k = 0; k < nB * d.K && herm; k++) herm = is_herm(B + 2 * (size_t)k * DD);
-    h->herm = herm ? 1 : 0;
-    // which of the scaled matrices -i dt A, -i dt B_j have a non-zero real / imaginary plane in ANY member
-    // (real plane of -i dt X = dt Im X, imaginary plane = -dt Re X): coefficient lists of the plane-wise DMMA assembly
-    unsigned lr = 0xffffffffu, li = 0xffffffffu;
-    int nr = 0, ni = 0;
-    for (int j = 0; j <= d.K; j++) {
-      bool any_re = false, any_im = false;
-      const int nsrc = j == 0 ? nA : nB;
-      for (int k = 0; k < nsrc; k++) {
-        const double* Mx = j == 0 ? A + 2 * (size_t)k * DD : B + 2 * ((size_t)k * d.K + (j - 1)) * DD;
-        for (size_t e = 0; e < DD; e++) { any_re = any_re || Mx[2 * e] != 0.0; any_im = any_im || Mx[2 * e + 1] != 0.0; }
-      }
-      if (any_im) { if (nr < 4) lr = (lr & ~(0xffu << (8 * nr))) | ((unsigned)j << (8 * nr)); nr++; }
-      if (any_re) { if (ni < 4) li = (li & ~(0xffu << (8 * ni))) | ((unsigned)j << (8 * ni)); ni++; }
-    }
-    h->asm_sparse = nr <= 4 && ni <= 4;
+    SystemStructure ss;
+    analyze_structure(d.D, d.K, nA, nB, A, B, ss);
+    h->herm = ss.herm;
+    h->asm_sparse = ss.asm_sparse;
     if (const char* e = getenv("QOC_ASM_SPARSE")) h->asm_sparse = h->asm_sparse && atoi(e) != 0;      // A/B testing
-    h->asm_lr = lr; h->asm_li = li;
-    // union over controls and members of the non-zero entries of -i dt B_j in the packed layout (flat entry = plane * 64 +
-    // 8 row + col): the trace-dots of the DMMA sweep contract only those (sweep_unitary_dmma_item)
-    // union over all matrices and members of the non-zero generator entries, per plane, in compact blocks of 8
+    h->asm_lr = ss.asm_lr; h->asm_li = ss.asm_li;
     h->asm_nblk = h->asm_nblk_re = 0;
-    if (h->dot_tab && d.D <= 8 && h->asm_sparse) {
-      bool used[128] = {};
-      for (int j = 0; j <= d.K; j++) {
-        const int nsrc = j == 0 ? nA : nB;
-        for (int k = 0; k < nsrc; k++) {
-          const double* Mx = j == 0 ? A + 2 * (size_t)k * DD : B + 2 * ((size_t)k * d.K + (j - 1)) * DD;
-          for (int c = 0; c < d.D; c++)
-            for (int r = 0; r < d.D; r++) {
-              const double* z = Mx + 2 * ((size_t)c * d.D + r);
-              if (z[1] != 0.0) used[8 * r + c] = true;
-              if (z[0] != 0.0) used[64 + 8 * r + c] = true;
-            }
-        }
-      }
-      int pos[128], n = 0, nre = 0;
-      for (int pl = 0; pl < 2; pl++) {
-        for (int f = 64 * pl; f < 64 * pl + 64; f++) if (used[f]) pos[n++] = f;
-        while (n % 8) pos[n++] = -1;
-        if (pl == 0) nre = n / 8;
-      }
-      const int nblk = n / 8;
-      for (int i = n; i < 128; i++) pos[i] = -1;
-      bool compact = nblk > 0 && nblk <= 12;                    // at least a quarter of the 16 natural blocks saved
-      if (const char* e = getenv("QOC_ASM_COMPACT")) compact = compact && atoi(e) != 0;      // A/B testing
-      if (compact) {
-        QOC_CUDA(h, cudaMemcpyAsync(h->dot_tab + 256, pos, sizeof(pos), cudaMemcpyHostToDevice, h->stream));
-        QOC_CUDA(h, cudaStreamSynchronize(h->stream));
-        h->asm_nblk = nblk; h->asm_nblk_re = nre;
-      }
-    }
     h->dot_nks = 0;
-    if (h->dot_tab && d.D <= 8 && d.K >= 1) {
-      bool used[128] = {};
-      for (int k = 0; k < nB; k++)
-        for (int j = 0; j < d.K; j++) {
-          const double* Mx = B + 2 * ((size_t)k * d.K + j) * DD;
-          for (int c = 0; c < d.D; c++)
-            for (int r = 0; r < d.D; r++) {
-              const double* z = Mx + 2 * ((size_t)c * d.D + r);
-              if (z[1] != 0.0) used[8 * r + c] = true;          // real plane of -i dt B = dt Im B
-              if (z[0] != 0.0) used[64 + 8 * r + c] = true;     // imaginary plane = -dt Re B
-            }
-        }
-      int tab[256], n = 0;
-      for (int f = 0; f < 128; f++) tab[f] = used[f] ? n++ : -1;
-      const int nks = ((n + 15) / 16) * 4;                      // four accumulator chains: a multiple of 4 k-steps
-      for (int sidx = 0; sidx < 128; sidx++) tab[128 + sidx] = -1;
-      for (int f = 0; f < 128; f++) if (tab[f] >= 0) tab[128 + tab[f]] = f;
-      bool sparse_dots = n > 0 && nks <= 24;                    // at least a quarter of the 32 dense k-steps saved
-      if (const char* e = getenv("QOC_DOTS_SPARSE")) sparse_dots = sparse_dots && atoi(e) != 0;      // A/B testing
-      if (sparse_dots) {
-        QOC_CUDA(h, cudaMemcpyAsync(h->dot_tab, tab, sizeof(tab), cudaMemcpyHostToDevice, h->stream));
-        QOC_CUDA(h, cudaStreamSynchronize(h->stream));
-        h->dot_nks = nks;
-      }
+    if (h->dot_tab && d.D <= 8) {
+      bool compact = h->asm_sparse && ss.asm_nblk > 0;
+      if (const char* e = getenv("QOC_ASM_COMPACT")) compact = compact && atoi(e) != 0;             // A/B testing
+      bool sparse_dots = d.K >= 1 && ss.dot_nks > 0;
+      if (const char* e = getenv("QOC_DOTS_SPARSE")) sparse_dots = sparse_dots && atoi(e) != 0;     // A/B testing
+      if (compact) QOC_CUDA(h, cudaMemcpyAsync(h->dot_tab + 256, ss.asm_pos, sizeof(ss.asm_pos), cudaMemcpyHostToDevice, h->stream));
+      if (sparse_dots) QOC_CUDA(h, cudaMemcpyAsync(h->dot_tab, ss.dot_tab, sizeof(ss.dot_tab), cudaMemcpyHostToDevice, h->stream));
+      QOC_CUDA(h, cudaStreamSynchronize(h->stream));            // `ss` leaves scope: the copies must have read it
+      if (compact) { h->asm_nblk = ss.asm_nblk; h->asm_nblk_re = ss.asm_nblk_re; }
+      if (sparse_dots) h->dot_nks = ss.dot_nks;
     }
   }
   auto upload = [&](const double* src, size_t count) -> int {

@@ -48,7 +48,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 // every 8x8x4 step costs 3 DMMA instead of 4 (K1 is accumulated once and seeds both the real and the imaginary accumulator);
 // the operand sums are one DADD per operand element (6 per 8x8 product) on the same FP64 pipe: 96 + 13 instead of 128 pipe
 // clocks per complex 8x8x8 product.  Normwise as accurate as the four-multiplication form (the imaginary part loses the
-// componentwise bound); observed parity vs the oracle stays at the 1e-14 level (tolerances 1e-10 / 1e-8).
+// componentwise bound); observed deviation from the CPU restatement of the reference: 1e-14 level (tolerances 1e-10 / 1e-8).
 #ifndef QOC_3M
 #define QOC_3M 1
 #endif

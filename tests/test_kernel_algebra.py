@@ -117,10 +117,11 @@ def test_infinity_norm_serves_the_taylor_bound():
 
 
 def _tables(members, D, K):
-    """numpy restatement of the structure analysis in qoc_set_system (csrc/qocgrape.cu): plane lists, compact assembly blocks,
-    compact dot slots.  Flat entry of the packed layout: plane * 64 + 8 row + col; the packed matrices are -i dt X, so their
-    real plane is dt Im X and their imaginary plane -dt Re X."""
+    """numpy restatement of analyze_structure (csrc/qocgrape.cu): plane lists, compact assembly blocks, compact dot slots.
+    Flat entry of the packed layout: plane * 64 + 8 row + col; the packed matrices are -i dt X, so their real plane is
+    dt Im X and their imaginary plane -dt Re X."""
     mats = [[m[0] for m in members]] + [[m[1][j] for m in members] for j in range(K)]
+    herm = all(np.array_equal(x, x.conj().T) for ms in mats for x in ms)
     lr = [j for j, ms in enumerate(mats) if any(np.any(x.imag != 0) for x in ms)]
     li = [j for j, ms in enumerate(mats) if any(np.any(x.real != 0) for x in ms)]
     used = np.zeros(128, bool)
@@ -135,18 +136,80 @@ def _tables(members, D, K):
                     if x[r, c].real != 0:
                         used[64 + 8 * r + c] = True
                         used_b[64 + 8 * r + c] |= j > 0
-    nblk_re = -(-int(used[:64].sum()) // 8)
-    nblk = nblk_re + -(-int(used[64:].sum()) // 8)
-    nks = -(-int(used_b.sum()) // 16) * 4
-    return lr, li, nblk_re, nblk, nks
+    pos = []
+    for pl in range(2):
+        pos += [f for f in range(64 * pl, 64 * pl + 64) if used[f]]
+        pos += [-1] * (-len(pos) % 8)
+        if pl == 0:
+            nblk_re = len(pos) // 8
+    nblk = len(pos) // 8
+    if not (0 < nblk <= 12):
+        nblk = nblk_re = 0
+    slots = [f for f in range(128) if used_b[f]]
+    nks = -(-len(slots) // 16) * 4
+    if not (len(slots) > 0 and nks <= 24):
+        nks = 0
+    return dict(herm=int(herm), sparse=int(len(lr) <= 4 and len(li) <= 4), lr=lr[:4], li=li[:4], nblk_re=nblk_re, nblk=nblk,
+                nks=nks, pos=pos, slots=slots)
+
+
+def _library_tables(members, D, K, shared=False):
+    import ctypes as C
+    import quoptimalcontrol_jl_b200 as qoc
+    lib = qoc._lib.load()
+    mem = members[:1] if shared else members
+    A = np.ascontiguousarray(np.stack([np.asarray(m[0], dtype=np.complex128).T for m in mem]))       # column-major
+    B = np.ascontiguousarray(np.stack([np.stack([np.asarray(b, dtype=np.complex128).T for b in m[1]]) for m in mem]))
+    out = (C.c_int * 392)()
+    flags = (qoc._lib.SHARED_A | qoc._lib.SHARED_B) if shared else 0
+    rc = lib.qoc_analyze_structure(D, K, len(members), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), flags, out)
+    assert rc == 0
+    o = np.array(out[:], dtype=np.int64)
+    unpack = lambda v: [b for b in ((int(v) >> (8 * i)) & 0xff for i in range(4)) if b != 0xff]
+    return dict(herm=int(o[0]), sparse=int(o[1]), lr=unpack(o[2]), li=unpack(o[3]), nblk_re=int(o[4]), nblk=int(o[5]), nks=int(o[6]),
+                pos=o[8:136], tab=o[136:392])
 
 
 def test_structure_tables_of_the_bench_config():
     """cfg4 (the bench default): 3 matrices with a real plane (sigma_y controls), 4 with an imaginary plane (diagonal drift,
     sigma_x controls) -> plane-wise assembly; 24 + 32 non-zero generator entries -> 3 + 4 compact blocks instead of 16;
-    48 non-zero control entries -> 12 dot k-steps instead of 32.  These are the counts DESIGN.md section 3.2 quotes."""
+    48 non-zero control entries -> 12 dot k-steps instead of 32.  These are the counts DESIGN.md section 3.2 quotes, from the
+    library's own analysis (qoc_analyze_structure runs without a GPU)."""
     import quoptimalcontrol_jl_b200 as qoc
     cfg = qoc.configs.config4(N=4, grid=3)
-    lr, li, nblk_re, nblk, nks = _tables(cfg["members"], 8, 6)
-    assert lr == [2, 4, 6] and li == [0, 1, 3, 5]
-    assert (nblk_re, nblk, nks) == (3, 7, 12)
+    t = _library_tables(cfg["members"], 8, 6)
+    assert t["herm"] == 1 and t["sparse"] == 1 and t["lr"] == [2, 4, 6] and t["li"] == [0, 1, 3, 5]
+    assert (t["nblk_re"], t["nblk"], t["nks"]) == (3, 7, 12)
+
+
+@pytest.mark.parametrize("kind,D", [("pauli", 8), ("pauli_k7", 8), ("real_sparse", 8), ("real_sparse", 6), ("mixed_member", 5),
+                                    ("dense", 8), ("dense", 7)])
+def test_structure_analysis_matches_its_restatement(kind, D):
+    """The library's structure analysis against the numpy restatement on the control structures of test_gpu_structure.py
+    (which runs the kernels these tables drive against the oracle)."""
+    from test_gpu_structure import _members
+    members = _members(kind, D, 12, seed=11 + D)
+    D = members[0][0].shape[0]
+    K = len(members[0][1])
+    t, r = _library_tables(members, D, K), _tables(members, D, K)
+    for key in ("herm", "sparse", "nblk_re", "nblk", "nks"):
+        assert t[key] == r[key], key
+    if r["sparse"]:
+        assert t["lr"] == r["lr"] and t["li"] == r["li"]
+    full = r["pos"] + [-1] * (128 - len(r["pos"]))
+    assert list(t["pos"]) == full                      # the positions are listed even when compaction is not worth it
+    assert [f for f in range(128) if t["tab"][f] >= 0] == r["slots"]
+    for sidx, f in enumerate(r["slots"]):
+        assert t["tab"][f] == sidx and t["tab"][128 + sidx] == f
+    assert all(t["tab"][128 + sidx] == -1 for sidx in range(len(r["slots"]), 128))
+
+
+def test_structure_analysis_of_shared_matrices_and_bad_arguments():
+    import ctypes as C
+    import quoptimalcontrol_jl_b200 as qoc
+    from test_gpu_structure import _members
+    members = _members("pauli", 8, 3, seed=3)
+    members = [members[0]] * 3
+    assert _library_tables(members, 8, 6, shared=True)["nks"] == _library_tables(members, 8, 6)["nks"] == 12
+    out = (C.c_int * 392)()
+    assert qoc._lib.load().qoc_analyze_structure(0, 1, 1, None, None, 0, out) == qoc._lib.QOC_EINVAL
