@@ -703,7 +703,8 @@ __global__ void __launch_bounds__(128, 5) chunk_expm_dmma_kernel(const PhasedPar
 // `reserve` of them are waiting (E and S work mixed on an SM use the FP64 pipe better than either alone, and a chain's
 // propagators are re-read while they still sit in L2).  Both queues are ticket
 // counters (one atomicAdd per item; a compare-and-swap claim serialises: one winner per L2 round trip, measured 0.7 us per
-// item).  An S ticket may be drawn before its entry is published; the holder waits for it.  That wait cannot deadlock: S
+// item).  An S ticket may be drawn before its entry is published; the holder waits for it (bounded to ~4 s: a producer that
+// never arrives yields NaN, not a hung GPU).  That wait cannot deadlock: S
 // tickets are drawn only once every E item has been claimed, and every unpublished entry depends only on E items that
 // resident CTAs are executing.  A list entry is (id + 1); the whole control block is zeroed by ONE memset node before the
 // launch.  Data written by other CTAs of the launch (chunk totals, boundary operators) is read with ld.global.cg after a
@@ -743,9 +744,17 @@ __global__ void __launch_bounds__(128, 5) closed_persistent_kernel(const PhasedP
         if (j < nE) {
           int v;
           unsigned backoff = 32;
-          while ((v = ld_vol(s_ready + j)) == 0) { __nanosleep(backoff); if (backoff < 256) backoff <<= 1; }
+          unsigned long long t_wait = 0;
+          while ((v = ld_vol(s_ready + j)) == 0) {
+            __nanosleep(backoff);
+            if (backoff < 256) backoff <<= 1;
+            const unsigned long long now = global_ns();
+            if (t_wait == 0) t_wait = now;
+            else if (now - t_wait > 4000000000ULL) break;      // ~4 s: the producer never arrived -- poison the result, do not hang the GPU
+          }
           __threadfence();
-          a = -(v - 1) - 2;
+          if (v > 0) a = -(v - 1) - 2;
+          else p.fomc[0] = __longlong_as_double(0x7ff8000000000000LL);      // a stays -1: this CTA leaves
         }
       }
       sh_item[0] = a;
