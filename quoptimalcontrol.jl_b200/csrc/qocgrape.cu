@@ -265,7 +265,9 @@ extern "C" int qoc_create(qoc_handle** out, const qoc_desc* desc) {
         CRC(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d.device));
         const long items = (long)h->n_groups * ((h->Cn + 3) / 4);
         h->persist_grid = (int)std::min<long>((long)sms * 5, items);
-        h->persist_reserve = h->persist_grid;                   // S items kept back for the tail (in units of items)
+        // sweep items are taken early only while more than `reserve` of them wait (never below the grid size: section 3.2 of
+        // DESIGN.md).  Default: all exponential items first -- mixing measured slower (0.302 vs 0.291 ms at 512 chains)
+        h->persist_reserve = 1 << 30;
         if (const char* e = getenv("QOC_PERSIST_RESERVE")) h->persist_reserve = (int)std::min<long>(1L << 30, std::max<long>(h->persist_grid, atol(e)));
         h->persist_ctl_bytes = (size_t)closed_persistent_ctl_ints(h->n_groups, h->Cn) * sizeof(int);
         CR(dev_alloc(h, (char**)&h->persist_ctl, h->persist_ctl_bytes));
