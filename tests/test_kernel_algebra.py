@@ -213,3 +213,88 @@ def test_structure_analysis_of_shared_matrices_and_bad_arguments():
     assert _library_tables(members, 8, 6, shared=True)["nks"] == _library_tables(members, 8, 6)["nks"] == 12
     out = (C.c_int * 392)()
     assert qoc._lib.load().qoc_analyze_structure(0, 1, 1, None, None, 0, out) == qoc._lib.QOC_EINVAL
+
+
+# ---- index maps of the tensor-pipe forms, emulated lane by lane ------------------------------------------------------------
+# DMMA.8x8x4 (mma.sync.m8n8k4.f64): lane (g = lane >> 2, q = lane & 3) supplies A[m = g][k = q] and B[k = q][n = g] and receives
+# D[m = g][n = 2 q], D[m = g][n = 2 q + 1].  Packed layout of a D <= 8 matrix X: flat entry f = plane * 64 + 8 row + col, lane
+# (g, q) holds rows g, columns 2 q, 2 q + 1 (f = 2 lane + e within a plane).
+def _dmma(acc, a_frag, b_frag):
+    """acc [8][8] += A [8][4] B [4][8] from per-lane fragments a_frag[lane], b_frag[lane]."""
+    A = np.zeros((8, 4)); B = np.zeros((4, 8))
+    for lane in range(32):
+        g, q = lane >> 2, lane & 3
+        A[g, q] = a_frag[lane]; B[q, g] = b_frag[lane]
+    return acc + A @ B
+
+
+def _packed(X, scale):
+    """flat [128] image of scale * X (8 x 8 complex): real plane then imaginary plane, entry 8 row + col."""
+    Z = scale * X
+    return np.concatenate([Z.real.reshape(-1), Z.imag.reshape(-1)])
+
+
+def test_compact_plane_wise_assembly_index_maps():
+    """chunk_expm_dmma_item, compact form: coefficient staging Ad[b][lane], amplitude fragments (list entry q of the block's
+    plane, slice g), scatter of D[m = g][n = slice] to flat position asm_pos[8 b + g] -- reproduces G_t = A~ + sum_j x[j,t] B~_j
+    for 8 slices, with every entry outside the union left at zero."""
+    import quoptimalcontrol_jl_b200 as qoc
+    cfg = qoc.configs.config4(N=8, grid=2)
+    A, Bs = cfg["members"][3][0], cfg["members"][3][1]
+    K, dt = len(Bs), cfg["T"] / cfg["N"]
+    t = _library_tables(cfg["members"], 8, K)
+    assert t["nblk"] == 7
+    sys_flat = [_packed(A, -1j * dt)] + [_packed(b, -1j * dt) for b in Bs]       # index 0 = drift, j = control j
+    x = RNG.uniform(-1, 1, (K, 8))
+    lists = [t["lr"] + [0xff] * (4 - len(t["lr"])), t["li"] + [0xff] * (4 - len(t["li"]))]
+    G = np.zeros((8, 128))                                                        # [slice][flat entry]
+    for b in range(t["nblk"]):
+        lst = lists[0] if b < t["nblk_re"] else lists[1]
+        a_frag, b_frag = np.zeros(32), np.zeros(32)
+        for lane in range(32):
+            g, q = lane >> 2, lane & 3
+            f, j = t["pos"][8 * b + g], lst[q]
+            a_frag[lane] = sys_flat[j][f] if (f >= 0 and j <= K) else 0.0
+            b_frag[lane] = 0.0 if j > K else (1.0 if j == 0 else x[j - 1, g])    # lane (g = slice, q = list entry)
+        Dm = _dmma(np.zeros((8, 8)), a_frag, b_frag)                              # [m = row of block][n = slice]
+        for g in range(8):
+            f = t["pos"][8 * b + g]
+            if f >= 0:
+                G[:, f] = Dm[g, :]
+    for s in range(8):
+        ref = _packed(A + sum(x[j, s] * Bs[j] for j in range(K)), -1j * dt)
+        assert np.max(np.abs(G[s] - ref)) < 1e-17
+
+
+def test_compact_trace_dot_index_maps():
+    """sweep_unitary_dmma_item, compact form: W staged at slot dot_tab[f], control fragments Bd[ks][lane (c, q)] =
+    B~flat[c][dot_tab[128 + 4 ks + q]], slice fragments W[slice g][slot 4 ks + q]; the accumulated chain gives
+    g[c][t] = sum_f B~flat[c][f] Wflat[t][f] = Re tr(conj(B~_c) .* W_t) summed over entries."""
+    import quoptimalcontrol_jl_b200 as qoc
+    cfg = qoc.configs.config4(N=8, grid=2)
+    Bs = cfg["members"][1][1]
+    K, dt = len(Bs), cfg["T"] / cfg["N"]
+    t = _library_tables(cfg["members"], 8, K)
+    nks = t["nks"]
+    assert nks == 12
+    Bflat = [_packed(b, -1j * dt) for b in Bs]
+    W = RNG.standard_normal((8, 8, 8)) + 1j * RNG.standard_normal((8, 8, 8))      # 8 slices
+    Wb = np.zeros((8, 4 * nks))                                                   # padding slots hold zeros
+    for s in range(8):
+        flat = _packed(W[s], 1.0)
+        for f in range(128):
+            if t["tab"][f] >= 0:
+                Wb[s, t["tab"][f]] = flat[f]
+    acc = np.zeros((8, 8))                                                        # [m = control][n = slice]
+    for ks in range(nks):
+        a_frag, b_frag = np.zeros(32), np.zeros(32)
+        for lane in range(32):
+            c, q = lane >> 2, lane & 3
+            f = t["tab"][128 + 4 * ks + q]
+            a_frag[lane] = Bflat[c][f] if (c < K and f >= 0) else 0.0
+            b_frag[lane] = Wb[c, 4 * ks + q]                                      # here g = slice index of the lane
+        acc = _dmma(acc, a_frag, b_frag)
+    for c in range(K):
+        for s in range(8):
+            ref = np.sum((np.conj(-1j * dt * Bs[c]) * W[s]).real)
+            assert abs(acc[c, s] - ref) < 1e-15
